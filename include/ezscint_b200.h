@@ -1,0 +1,123 @@
+/*
+ * include/ezscint_b200.h -- C ABI of libezb200.so, the B200-native drop-in for librmn's EZ interpolator
+ * hot path (c_ezdefset / c_ezsint / c_ezuvint / c_ezsetopt and the grid-definition calls they need).
+ *
+ * Every entry point below keeps the name, argument order, argument meaning and return codes of the
+ * reference declaration it replaces; the reference line is cited beside it
+ * (ref = /root/reference/src/PUBLIC_INCLUDES/rmn/ezscint.h unless another file is named).
+ * Fortran bindings use the reference's mangling: trailing underscore, all arguments by reference, hidden
+ * string lengths last as int32 (rpnmacros.h:21,27-45).
+ *
+ * Pointer convention (additive to the reference): every field / coordinate pointer may be a HOST pointer
+ * (pageable or pinned; the library stages it through HBM, as a stock caller expects) or a DEVICE pointer
+ * on the current CUDA device (used in place, no copies).  Grids, gridsets (x, y, zone bits), axes and
+ * Newton tables stay resident in HBM between calls.  No torch types cross this boundary.
+ */
+#ifndef EZSCINT_B200_H
+#define EZSCINT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef const int32_t F2Cl;
+
+/* ---- gridset selection ------------------------------------------------------------------------ */
+int32_t c_ezdefset(int32_t gdout, int32_t gdin);                                   /* ref :11  (ezdefset.c:38)  -> 1 */
+int32_t ezdefset_(int32_t *gdout, int32_t *gdin);                                  /* ref :10 */
+int32_t c_ezgetgdin(void);                                                         /* ref :186 */
+int32_t c_ezgetgdout(void);                                                        /* ref :187 */
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+int32_t c_ezsint(float *zout, float *zin);                                         /* ref :87  (ezsint.c:38)   -> 0 | 2 | 1 | -1 */
+int32_t ezsint_(float *zout, float *zin);                                          /* ref :86 */
+int32_t c_ezuvint(float *uuout, float *vvout, float *uuin, float *vvin);           /* ref :90  (ezuvint.c:32)  -> 0 | 2 | -1 */
+int32_t ezuvint_(float *uuout, float *vvout, float *uuin, float *vvin);            /* ref :89 */
+int32_t c_ezwdint(float *spdout, float *wdout, float *uuin, float *vvin);          /* ref :93  (ezwdint.c:36) */
+int32_t ezwdint_(float *spdout, float *wdout, float *uuin, float *vvin);           /* ref :92 */
+int     c_ezsint_mask(int *mask_out, int *mask_in);                                /* ref :164 (ez_mask.c:184) */
+int     ezsint_mask_(int *mask_out, int *mask_in);                                 /* ref :163 */
+
+/* ---- options ---------------------------------------------------------------------------------- */
+int32_t c_ezsetopt(char *option, char *value);                                     /* ref :78  (ezsetopt.c:59) -> 0 | -1 */
+int32_t ezsetopt_(char *option, char *value, F2Cl lenoption, F2Cl lenvalue);       /* ref :77 */
+int32_t c_ezsetval(char *option, float fvalue);                                    /* ref :84  (ezsetval.c:115) */
+int32_t ezsetval_(char *option, float *fvalue, F2Cl lenoption);                    /* ref :83 */
+int32_t c_ezsetival(char *option, int32_t ivalue);                                 /* ref :81  (ezsetval.c:121) */
+int32_t ezsetival_(char *option, int32_t *ivalue, F2Cl lenoption);                 /* ref :80 */
+int32_t c_ezgetopt(char *option, char *value);                                     /* ref :35  (ezgetopt.c:53) */
+int32_t ezgetopt_(char *option, char *value, F2Cl lenoption, F2Cl lenvalue);       /* ref :34 */
+int32_t c_ezgetval(char *option, float *value);                                    /* ref :41  (ezgetval.c:55) */
+int32_t ezgetval_(char *option, float *value, F2Cl lenoption);                     /* ref :40 */
+int32_t c_ezgetival(char *option, int32_t *value);                                 /* ref :38  (ezgetval.c:89) */
+int32_t ezgetival_(char *option, int32_t *value, F2Cl lenoption);                  /* ref :37 */
+
+/* ---- grid definition -------------------------------------------------------------------------- */
+int32_t c_ezgdef_fmem(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4,
+                      float *ax, float *ay);                                       /* ref :28  (ezgdef_fmem.c:37) -> gdid */
+int32_t ezgdef_fmem_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
+                     float *ax, float *ay, F2Cl lengrtyp, F2Cl lengrref);          /* ref :26 */
+int32_t c_ezgdef(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4,
+                 float *ax, float *ay);                                            /* ref :15  (ezgdef.c:50); "FILE" sources -> -1 */
+int32_t ezgdef_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
+                float *ax, float *ay, F2Cl lengrtyp, F2Cl lengrref);               /* ref :13 */
+int32_t c_ezqkdef(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit);
+                                                                                   /* ref :66  (ezqkdef.c:25); regular types only, '#','Y','Z','U' need an FST file -> -1 */
+int32_t ezqkdef_(int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, int32_t *iunit,
+                 F2Cl lengrtyp);                                                   /* ref :64 */
+int32_t c_ezgdef_supergrid(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t vercode, int32_t nsubgrids, int32_t *subgrid);
+                                                                                   /* ref :32  (ezgdef_supergrid.c:40) */
+int32_t ezgdef_supergrid_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *vercode, int32_t *nsubgrids, int32_t *subgrid,
+                          F2Cl lengrtyp, F2Cl lengrref);                           /* ref :31 */
+int32_t c_gdrls(int32_t gdin);                                                     /* ref :75  (gdrls.c:88) */
+int32_t gdrls_(int32_t *gdin);                                                     /* ref :74 */
+
+/* ---- grid queries ----------------------------------------------------------------------------- */
+int32_t c_ezgprm(int32_t gdid, char *grtyp, int32_t *ni, int32_t *nj, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4);  /* ref :51 */
+int32_t ezgprm_(int32_t *gdid, char *grtyp, int32_t *ni, int32_t *nj, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, F2Cl l);
+int32_t c_ezgxprm(int32_t gdid, int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
+                  char *grref, int32_t *ig1ref, int32_t *ig2ref, int32_t *ig3ref, int32_t *ig4ref);                             /* ref :57 */
+int32_t ezgxprm_(int32_t *gdid, int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
+                 char *grref, int32_t *ig1ref, int32_t *ig2ref, int32_t *ig3ref, int32_t *ig4ref, F2Cl l1, F2Cl l2);
+int32_t c_ezget_nsubgrids(int32_t gdid);                                           /* ref :169 */
+int32_t ezget_nsubgrids_(int32_t *gdid);
+int32_t c_ezget_subgridids(int32_t gdid, int32_t *subgrid);                        /* ref :172 */
+int32_t ezget_subgridids_(int32_t *gdid, int32_t *subgrid);
+int32_t c_gdll(int32_t gdid, float *lat, float *lon);                              /* ref :62  (gdll.c:47) */
+int32_t gdll_(int32_t *gdid, float *lat, float *lon);
+int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int32_t n);   /* ref :138 (gdxyfll.c:190) */
+int32_t gdxyfll_(int32_t *gdid, float *x, float *y, float *lat, float *lon, int32_t *n);
+int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n); /* ref :117 (gdxysval.c:50) */
+int32_t gdxysval_(int32_t *gdin, float *zout, float *zin, float *x, float *y, int32_t *n);
+int     c_gdsetmask(int gdid, int *mask);                                          /* ref :146 (ez_mask.c:67) */
+int     gdsetmask_(int *gdid, int *mask);
+int     c_gdgetmask(int gdid, int *mask);                                          /* ref :149 (ez_mask.c:89) */
+int     gdgetmask_(int *gdid, int *mask);
+
+/* ---- descriptor helpers callers use to build ig1..ig4 (Fortran ABI only in the reference) ------- */
+void cxgaig_(char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
+             float *xg1, float *xg2, float *xg3, float *xg4, F2Cl l);              /* src/base/xgaig.f90:4 */
+void cigaxg_(char *grtyp, float *xg1, float *xg2, float *xg3, float *xg4,
+             const int32_t *ig1, const int32_t *ig2, const int32_t *ig3, const int32_t *ig4, F2Cl l);   /* src/base/igaxg.f90:5 */
+
+/* ---- additive entry points (not in the reference) ---------------------------------------------- */
+/* nfields fields laid out back to back (ni*nj of gdin / gdout each); x, y and zone bits are read once for the batch */
+int32_t c_ezsint_batch(float *zout, float *zin, int32_t nfields);
+int32_t c_ezuvint_batch(float *uuout, float *vvout, float *uuin, float *vvin, int32_t nfields);
+/* CUDA stream (cudaStream_t as void*) used by the calling thread's launches; NULL = default stream */
+int32_t c_ezb200_set_stream(void *stream);
+/* 0 = reference evaluation order (bit-parity), 1 = fp64 weight form (default); per calling thread */
+int32_t c_ezb200_set_arith(int32_t mode);
+int32_t c_ezb200_get_arith(void);
+/* copy the cached gridset of (gdout, gdin) to host arrays (any may be NULL): x, y [npts], zone bits [npts], counts[6] */
+int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, uint8_t *zonebits, int32_t *counts);
+/* number of CUDA kernels launched by the calling thread since the last call with reset != 0 */
+int64_t c_ezb200_launch_count(int32_t reset);
+/* block until the calling thread's stream is idle ; returns 0 or -1 with the CUDA error on stderr */
+int32_t c_ezb200_sync(void);
+const char *c_ezb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1488 @@
+// librmn_b200/csrc/ez_host.cu -- host logic of libezb200.so: grid registry, per-thread session and options,
+// the device-resident gridset cache, and the C-ABI entry points declared in include/ezscint_b200.h.
+//
+// This is the L3 layer of the reference (src/interp/*.c: Grille[][] registry, gset cache, options, dispatch)
+// re-designed for a GPU: the registry holds *descriptors*; everything per-point (lat/lon of the target, x/y
+// in source index space, zone bits, Yin-Yang panel) is built by kernels once per (source,target) pair and
+// kept in HBM; c_ezsint / c_ezuvint then cost one (batched) gather kernel plus, when poles or outside
+// points exist, a tiny per-field pre-pass.  There is no CPU fallback: if no CUDA device is usable the
+// compute entry points print the CUDA error and return -1.
+#include <cuda_runtime.h>
+#include <ctype.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ezscint_b200.h"
+#include "ez_hostmath.h"
+#include "ez_kernels.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// data model
+// ---------------------------------------------------------------------------------------------------
+struct Options {   // _groptions, ez_def.h:225-243 ; defaults ez_statics.c:17
+    int degre_interp = EZ_CUBIC;
+    int degre_extrap = EZ_MAXIMUM;
+    int use_1subgrid = 0;
+    int valeur_1subgrid = -1;
+    int verbose = 0;
+    int polar_correction = 1;
+    int wgt_num = 16;
+    int msg_pt_tol = 0;
+    int cld_interp_alg = 4;   // DISTANCE
+    float msg_gridpt_dist = 0.5f;
+    float msg_dist_thresh = 3.0f;
+    float valeur_extrap = 0.0f;
+};
+
+struct Gset {   // _gridset, ez_def.h:148-166, device-resident
+    int gdin = -1;
+    bool built = false;
+    bool yy = false;            // source is a 'U' supergrid: zb carries the panel bit, no zones
+    float *d_x = nullptr, *d_y = nullptr;
+    uint8_t *d_zb = nullptr;
+    int counts[6] = {0, 0, 0, 0, 0, 0};   // DEHORS, AU_NORD, AU_SUD, POLE_NORD, POLE_SUD, yang
+};
+
+struct Grid {   // _Grille, ez_def.h:196-222
+    int id = -1;
+    bool alive = true;
+    int access_count = 1;
+    char grtyp = 0, grref = 0;
+    int ni = 0, nj = 0;
+    int ig[4] = {0, 0, 0, 0}, igref[4] = {0, 0, 0, 0};
+    float xg[4] = {0, 0, 0, 0}, xgref[4] = {0, 0, 0, 0};
+    float llp[4] = {0, 0, 0, 0}, xyp[4] = {0, 0, 0, 0};
+    float r[9] = {0}, ri[9] = {0};
+    int i1 = 1, i2 = 0, j1 = 1, j2 = 0, extension = 0, needs_expansion = 0, axe_y_inverse = 0, hemisphere = 0;
+    std::vector<float> ax, ay, ncx, ncy;   // host copies (the library owns them, ez_defaxes.c:49-53)
+    int nsubgrids = 0;
+    int subgrid[2] = {-1, -1};
+    int mymaskgrid = -1, mi0 = 0, mi1 = 0, mj0 = 0, mj1 = 0;
+    std::vector<int> mask;
+    bool has_mask = false;
+    // device side
+    int device = -1;
+    float *d_ax = nullptr, *d_ay = nullptr, *d_cx = nullptr, *d_cy = nullptr;
+    float *d_lat = nullptr, *d_lon = nullptr;   // flag LAT
+    std::map<int, std::unique_ptr<Gset>> gsets; // keyed by gdin (this grid is the target)
+};
+
+std::recursive_mutex g_mtx;
+std::vector<std::unique_ptr<Grid>> g_grids;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void *get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return nullptr; }
+            cap = bytes;
+        }
+        return p;
+    }
+};
+
+struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus per-thread CUDA state
+    int gdin = -1, gdout = -1;
+    Options opt;
+    cudaStream_t stream = 0;
+    int arith = 1;
+    long launches = 0;
+    DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4];
+};
+thread_local Session S;
+
+#define CUDA_OK(call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fprintf(stderr, "<ezb200> CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+            return -1;                                                                              \
+        }                                                                                           \
+    } while (0)
+
+Grid *grid_of(int gdid) {
+    if (gdid < 0 || gdid >= (int)g_grids.size()) return nullptr;
+    Grid *g = g_grids[gdid].get();
+    return (g && g->alive) ? g : nullptr;
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+template <class T>
+int dev_alloc(T **p, size_t n) {
+    CUDA_OK(cudaMalloc((void **)p, n * sizeof(T)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// grid definition (host)
+// ---------------------------------------------------------------------------------------------------
+
+// ez_xpncof.c:48-226
+void xpncof(Grid &g) {
+    g.i1 = 1;
+    g.i2 = g.ni;
+    const int ni = g.ni, nj = g.nj;
+    switch (g.grtyp) {
+        case '!': case 'N': case 'S': case 'T':
+            g.j1 = 1; g.j2 = nj; g.extension = 0;
+            break;
+        case 'L': {
+            g.extension = 0; g.j1 = 1; g.j2 = nj;
+            float x[4];
+            ezh::cigaxg('L', x, g.ig);
+            float first_lat = x[0], first_lon = x[1], dlat = x[2], dlon = x[3];
+            if ((first_lat - dlat) > (-90.0 + 0.01 * dlat)) break;
+            float last_lat = first_lat + (nj - 1) * dlat;
+            if ((last_lat + dlat) < (90.0 - 0.01 * dlat)) break;
+            if (first_lon < 0.0) first_lon += 360.0;
+            float last_lon = first_lon + (dlon * (ni - 1));
+            if ((last_lon - first_lon) > (360 - 0.01 * dlon)) { g.extension = 1; break; }
+            float extra_lon = last_lon + dlon;
+            if ((extra_lon - first_lon) > (360.0 - dlon * 0.01)) g.extension = 2;
+            break;
+        }
+        case 'A': case 'G':
+            g.extension = 2;
+            if (g.ig[0] == 0) { g.j1 = 1; g.j2 = nj; }
+            else if (g.ig[0] == 1) { g.j1 = -nj + 1; g.j2 = nj; }
+            else if (g.ig[0] == 2) { g.j1 = 1; g.j2 = 2 * nj; }
+            break;
+        case 'B':
+            g.extension = 1;
+            if (g.ig[0] == 0) { g.j1 = 1; g.j2 = nj; }
+            else if (g.ig[0] == 1) { g.j1 = -nj + 2; g.j2 = nj; }
+            else if (g.ig[0] == 2) { g.j1 = 1; g.j2 = 2 * nj - 1; }
+            break;
+        case 'E':
+            g.j1 = 1; g.j2 = nj;   // `extension` is never assigned for 'E' (ez_xpncof.c:152-155): stays 0
+            break;
+        case '#': case 'Z':
+            if (g.ax.empty() || g.ay.empty()) { g.j1 = 1; g.j2 = nj; g.extension = 0; break; }
+            switch (g.grref) {
+                case 'E':
+                    g.j1 = 1; g.j2 = nj;
+                    g.extension = ((g.ax[ni - 1] - g.ax[0]) < 359.0) ? 0 : 1;
+                    break;
+                case 'L': {
+                    g.extension = 0; g.j1 = 1; g.j2 = nj;
+                    float first_lat = g.ay[0], last_lat = g.ay[nj - 1];
+                    float dlat = g.ay[1] - g.ay[0];
+                    if ((first_lat - dlat) > (-90.0 + 0.01 * dlat)) break;
+                    dlat = g.ay[nj - 1] - g.ay[nj - 2];
+                    if ((last_lat + dlat) < (90.0 - 0.01 * dlat)) break;
+                    float first_lon = g.ax[0], last_lon = g.ax[ni - 1];
+                    float dlon = g.ax[ni - 1] - g.ax[ni - 2];
+                    if ((last_lon - first_lon) > (360.0 - 0.01 * dlon)) {
+                        g.extension = 1;
+                    } else {
+                        float extra_lon = last_lon + dlon;
+                        if ((extra_lon - first_lon) > (360.0 - 0.01 * dlon)) g.extension = 2;
+                    }
+                    break;
+                }
+                default:
+                    g.j1 = 1; g.j2 = nj; g.extension = 0;
+                    break;
+            }
+            break;
+        default:
+            g.j1 = 1; g.j2 = nj; g.extension = 0;
+            break;
+    }
+}
+
+// c_ezdefxg, ez_defxg.c:28-165 (+ the fp32 parameter sets ez_ll2rgd.inc:70-118 derives per call)
+void defxg(Grid &g) {
+    const int ni = g.ni, nj = g.nj;
+    switch (g.grtyp) {
+        case 'A': case 'G':
+            g.xg[3] = 360. / ni;   // DLON (double division, stored fp32)
+            g.xg[1] = 0.0;         // SWLON
+            switch (g.ig[0]) {
+                case 0: g.xg[2] = 180. / nj; g.xg[0] = -90. + 0.5 * g.xg[2]; break;
+                case 1: g.xg[2] = 90. / nj; g.xg[0] = 0.5 * g.xg[2]; g.needs_expansion = 1; break;
+                case 2: g.xg[2] = 90. / nj; g.xg[0] = -90. + 0.5 * g.xg[2]; g.needs_expansion = 1; break;
+                default: fprintf(stderr, "<ez_gdef_fmem> 'A' grid has to be Global/North/South\n"); break;
+            }
+            if (g.ig[1] == 1) g.axe_y_inverse = 1;
+            break;
+        case 'B':
+            g.xg[3] = 360. / (ni - 1);
+            g.xg[1] = 0.0;
+            switch (g.ig[0]) {
+                case 0: g.xg[2] = 180. / (nj - 1); g.xg[0] = -90.; break;
+                case 1: g.xg[2] = 90. / (nj - 1); g.xg[0] = 0.; g.needs_expansion = 1; break;
+                case 2: g.xg[2] = 90. / (nj - 1); g.xg[0] = -90.; g.needs_expansion = 1; break;
+                default: fprintf(stderr, "<ezgdef_fmem> 'B' grid has to be Global/North/South\n"); break;
+            }
+            if (g.ig[1] == 1) g.axe_y_inverse = 1;
+            break;
+        case 'E':
+            ezh::cigaxg('E', g.xg, g.ig);
+            break;
+        case '#': case 'Z':
+            if (g.grref == 'N') g.hemisphere = 1;
+            if (g.grref == 'S') g.hemisphere = 2;
+            if (g.grref == 'E') ezh::cigaxg('E', g.xgref, g.igref);
+            break;
+        case 'L':
+            ezh::cigaxg('L', g.xg, g.ig);
+            break;
+        case 'N':
+            ezh::cigaxg('N', g.xg, g.ig);
+            g.hemisphere = 1;
+            break;
+        case 'S':
+            ezh::cigaxg('S', g.xg, g.ig);
+            g.hemisphere = 2;
+            break;
+        default:
+            break;
+    }
+}
+
+// parameters the kernels need beyond xg/xgref
+void derive_params(Grid &g) {
+    const int ni = g.ni, nj = g.nj;
+    // ez_calclatlon's grll arguments
+    if (g.grtyp == 'A' || g.grtyp == 'B' || g.grtyp == 'L') {
+        for (int k = 0; k < 4; k++) g.llp[k] = g.xg[k];
+    } else if (g.grtyp == 'E') {
+        float dlon = 360. / (ni - 1);            // ez_calclatlon.c:64-67
+        float dlat = 180. / (nj);
+        g.llp[0] = -90. + 0.5 * dlat;
+        g.llp[1] = 0.0f;
+        g.llp[2] = dlat;
+        g.llp[3] = dlon;
+    }
+    // ez_ll2rgd's fp32 (xlat0, xlon0, dellat, dellon)
+    if (g.grtyp == 'L') {
+        for (int k = 0; k < 4; k++) g.xyp[k] = g.xg[k];
+    } else if (g.grtyp == 'A') {
+        float dellon = 360.0f / (float)ni, dellat = 0.f, xlat0 = 0.f;
+        if (g.ig[0] == 0) { dellat = 180.0f / (float)nj; xlat0 = -90.0f + dellat * 0.5f; }
+        if (g.ig[0] == 1) { dellat = 90.0f / (float)nj; xlat0 = dellat * 0.5f; }
+        if (g.ig[0] == 2) { dellat = 90.0f / (float)nj; xlat0 = -90.0f + dellat * 0.5f; }
+        g.xyp[0] = xlat0; g.xyp[1] = 0.0f; g.xyp[2] = dellat; g.xyp[3] = dellon;
+    } else if (g.grtyp == 'B') {
+        float dellon = 360.0f / (float)(ni - 1), dellat = 0.f, xlat0 = 0.f;
+        if (g.ig[0] == 0) { dellat = 180.0f / (float)(nj - 1); xlat0 = -90.0f; }
+        if (g.ig[0] == 1) { dellat = 90.0f / (float)(nj - 1); xlat0 = 0.0f; }
+        if (g.ig[0] == 2) { dellat = 90.0f / (float)(nj - 1); xlat0 = -90.0f; }
+        g.xyp[0] = xlat0; g.xyp[1] = 0.0f; g.xyp[2] = dellat; g.xyp[3] = dellon;
+    }
+    // rotation matrices: ez_crot(r, ri, xlon1, xlat1, xlon2, xlat2) with (xlat1,xlon1,xlat2,xlon2) = xg / xgref
+    if (g.grtyp == 'E') ezh::crot(g.r, g.ri, g.xg[1], g.xg[0], g.xg[3], g.xg[2]);
+    if ((g.grtyp == 'Z' || g.grtyp == '#') && g.grref == 'E') ezh::crot(g.r, g.ri, g.xgref[1], g.xgref[0], g.xgref[3], g.xgref[2]);
+}
+
+int calcntncof(Grid &g) {   // ez_calcntncof.c:29-54
+    if (g.grtyp == 'Y' || !g.ncx.empty()) return 0;
+    int nnj = g.j2 - g.j1 + 1;
+    g.ncx.assign((size_t)g.ni * 6, 1.0f);
+    g.ncy.assign((size_t)nnj * 6, 1.0f);
+    if (!ezh::nwtncof(g.ncx.data(), g.ncy.data(), g.ax.data(), g.ay.data(), g.ni, g.nj, g.j1, g.j2, g.extension)) return -1;
+    return 0;
+}
+
+// c_ezdefaxes, ez_defaxes.c:31-114
+int defaxes(Grid &g, const float *ax, const float *ay) {
+    switch (g.grtyp) {
+        case '#': case 'Z':
+            ezh::cigaxg(g.grref, g.xgref, g.igref);
+            g.ax.assign(ax, ax + g.ni);
+            g.ay.assign(ay, ay + g.nj);
+            xpncof(g);
+            if (calcntncof(g) < 0) return -1;
+            break;
+        case 'Y':
+            g.ax.assign(ax, ax + (size_t)g.ni * g.nj);
+            g.ay.assign(ay, ay + (size_t)g.ni * g.nj);
+            xpncof(g);
+            break;
+        case 'G': {
+            g.grref = 'L';
+            g.xgref[0] = 0.0f; g.xgref[1] = 0.0f; g.xgref[2] = 1.0f; g.xgref[3] = 1.0f;
+            ezh::cxgaig('L', g.igref, g.xgref);
+            g.ax.resize(g.ni);
+            float dlon = 360. / (float)g.ni;
+            for (int i = 0; i < g.ni; i++) g.ax[i] = (float)i * dlon;
+            xpncof(g);
+            int nlat = (g.ig[0] == 0) ? g.nj : 2 * g.nj;
+            g.ay.resize(nlat);
+            ezh::glat(g.ay.data(), nlat);
+            if (calcntncof(g) < 0) return -1;
+            break;
+        }
+        default:
+            xpncof(g);
+            break;
+    }
+    return 0;
+}
+
+bool same_axes(const std::vector<float> &a, const float *b, size_t n) {
+    if (a.size() < n) return false;
+    for (size_t i = 0; i < n; i++)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+// registry lookup with the reference's identity rules (ez_findgrid.c:49-130)
+int find_grid(char grtyp, char grref, int ni, int nj, const int ig[4], const int igref[4], const float *ax, const float *ay, bool irregular) {
+    for (auto &up : g_grids) {
+        Grid *g = up.get();
+        if (!g || !g->alive || g->nsubgrids > 0) continue;
+        if (g->grtyp != grtyp || g->ni != ni || g->nj != nj) continue;
+        if (memcmp(g->ig, ig, sizeof(int) * 4) != 0) continue;
+        if (grtyp == 'G') return g->id;
+        if (!irregular) return g->id;
+        if (g->grref != grref || memcmp(g->igref, igref, sizeof(int) * 4) != 0) continue;
+        size_t nx = (grtyp == 'Y') ? (size_t)ni * nj : (size_t)ni, ny = (grtyp == 'Y') ? (size_t)ni * nj : (size_t)nj;
+        if (ax && ay && same_axes(g->ax, ax, nx) && same_axes(g->ay, ay, ny)) return g->id;
+    }
+    return -1;
+}
+
+int add_grid(std::unique_ptr<Grid> g) {
+    g->id = (int)g_grids.size();
+    g_grids.push_back(std::move(g));
+    return g_grids.back()->id;
+}
+
+int gdef_fmem(int ni, int nj, const char *grtyp, const char *grref, int ig1, int ig2, int ig3, int ig4, const float *ax, const float *ay) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    const char t = grtyp[0];
+    const int ig[4] = {ig1, ig2, ig3, ig4};
+    if (ni <= 0 || nj <= 0) {
+        fprintf(stderr, "<c_ezgdef_fmem> invalid dimensions %d x %d\n", ni, nj);
+        return -1;
+    }
+    const bool irregular = (t == '#' || t == 'Y' || t == 'Z' || t == 'G');
+    if (irregular) {
+        if (t != 'G' && (!ax || !ay)) {
+            fprintf(stderr, "<c_ezgdef_fmem> grid type '%c' needs ax and ay\n", t);
+            return -1;
+        }
+        const char rr = grref ? grref[0] : ' ';
+        // 'G' grids are matched on (ni,nj,ig) alone (ez_findgrid.c:53-57)
+        int found = find_grid(t, (t == 'G') ? 'L' : rr, ni, nj, ig, ig, ax, ay, t != 'G');
+        if (found >= 0) {
+            g_grids[found]->access_count++;
+            return found;
+        }
+        auto g = std::make_unique<Grid>();
+        g->grtyp = t;
+        g->grref = rr;
+        g->ni = ni;
+        g->nj = nj;
+        for (int k = 0; k < 4; k++) { g->ig[k] = ig[k]; g->igref[k] = ig[k]; }
+        g->i1 = 1; g->i2 = ni; g->j1 = 1; g->j2 = nj;
+        defxg(*g);
+        if (defaxes(*g, ax, ay) < 0) return -1;
+        xpncof(*g);
+        derive_params(*g);
+        return add_grid(std::move(g));
+    }
+    if (!(t == 'A' || t == 'B' || t == 'E' || t == 'L' || t == 'N' || t == 'S')) {
+        fprintf(stderr, "<c_ezgdef_fmem> grid type '%c' is outside the B200 hot-path scope (L/N/S/E/A/B/G/Z/#/Y/U)\n", t);
+        return -1;
+    }
+    const int zero[4] = {0, 0, 0, 0};
+    int found = find_grid(t, 0, ni, nj, ig, zero, nullptr, nullptr, false);
+    if (found >= 0) {
+        g_grids[found]->access_count++;
+        return found;
+    }
+    auto g = std::make_unique<Grid>();
+    g->grtyp = t;
+    g->grref = 0;   // c_ezidentify_reg_grid, ez_identifygrid.c:63
+    g->ni = ni;
+    g->nj = nj;
+    for (int k = 0; k < 4; k++) g->ig[k] = ig[k];
+    defxg(*g);
+    xpncof(*g);
+    derive_params(*g);
+    return add_grid(std::move(g));
+}
+
+// c_ezgdef_yymask, ezgdef_yymask.c:27-69
+void gdef_yymask(Grid &sub) {
+    int k = 0, i0 = 0, i1 = 0;
+    for (int i = 0; i < sub.ni; i++)
+        if (sub.ax[i] >= 45.0 && sub.ax[i] <= 315.0) { k++; if (k == 1) i0 = i; i1 = i; }
+    int yni = k, j0 = 0, j1 = 0;
+    k = 0;
+    for (int j = 0; j < sub.nj; j++)
+        if (sub.ay[j] >= -45.0 && sub.ay[j] <= 45.0) { k++; if (k == 1) j0 = j; j1 = j; }
+    int ynj = k;
+    char t[2] = {sub.grtyp, 0}, r[2] = {sub.grref, 0};
+    std::vector<float> mx(sub.ax.begin() + i0, sub.ax.begin() + i0 + yni), my(sub.ay.begin() + j0, sub.ay.begin() + j0 + ynj);
+    int sid = sub.id;
+    int mid = gdef_fmem(yni, ynj, t, r, sub.igref[0], sub.igref[1], sub.igref[2], sub.igref[3], mx.data(), my.data());
+    Grid *s = grid_of(sid);   // g_grids may have been reallocated
+    s->mymaskgrid = mid;
+    s->mi0 = i0; s->mi1 = i1; s->mj0 = j0; s->mj1 = j1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device mirrors
+// ---------------------------------------------------------------------------------------------------
+int ensure_device(Grid &g) {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (g.device == dev) return 0;
+    if (g.device >= 0 && g.device != dev) {
+        fprintf(stderr, "<ezb200> grid %d was built on CUDA device %d but the current device is %d (one process per GPU)\n", g.id, g.device, dev);
+        return -1;
+    }
+    auto up = [&](float **d, const std::vector<float> &h) -> int {
+        if (h.empty()) return 0;
+        CUDA_OK(cudaMalloc((void **)d, h.size() * sizeof(float)));
+        CUDA_OK(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (up(&g.d_ax, g.ax) < 0 || up(&g.d_ay, g.ay) < 0 || up(&g.d_cx, g.ncx) < 0 || up(&g.d_cy, g.ncy) < 0) return -1;
+    g.device = dev;
+    return 0;
+}
+
+GridDev to_dev(const Grid &g) {
+    GridDev d;
+    memset(&d, 0, sizeof(d));
+    d.grtyp = g.grtyp; d.grref = g.grref;
+    d.ni = g.ni; d.nj = g.nj; d.i1 = g.i1; d.i2 = g.i2; d.j1 = g.j1; d.j2 = g.j2;
+    d.ext = g.extension;
+    d.xpn = XPN_NONE;
+    if (g.needs_expansion) {
+        if (g.grtyp == 'A' || g.grtyp == 'G') d.xpn = (g.ig[0] == 1) ? XPN_AG_NORTH : XPN_AG_SOUTH;
+        if (g.grtyp == 'B') d.xpn = (g.ig[0] == 1) ? XPN_B_NORTH : XPN_B_SOUTH;
+    }
+    d.yinv = g.axe_y_inverse;
+    d.hemisphere = g.hemisphere;
+    for (int k = 0; k < 4; k++) {
+        d.ig[k] = g.ig[k]; d.igref[k] = g.igref[k]; d.xg[k] = g.xg[k]; d.xgref[k] = g.xgref[k]; d.llp[k] = g.llp[k]; d.xyp[k] = g.xyp[k];
+    }
+    for (int k = 0; k < 9; k++) { d.r[k] = g.r[k]; d.ri[k] = g.ri[k]; }
+    d.ax = g.d_ax; d.ay = g.d_ay; d.cx = g.d_cx; d.cy = g.d_cy;
+    return d;
+}
+
+// ez_calclatlon, ez_calclatlon.c:30 (flag LAT): device-resident lat/lon of every grid point
+int ensure_latlon(Grid &g) {
+    if (g.d_lat) return 0;
+    if (g.grtyp == 'Y' && (g.grref == 'N' || g.grref == 'S' || g.grref == 'E')) {
+        fprintf(stderr, "<ez_calclatlon> Operation not supported - Y grid on %c Grid\n", g.grref);
+        return -1;
+    }
+    if (ensure_device(g) < 0) return -1;
+    size_t n = (size_t)g.ni * g.nj;
+    if (dev_alloc(&g.d_lat, n) < 0 || dev_alloc(&g.d_lon, n) < 0) return -1;
+    ezk::calclatlon(to_dev(g), g.d_lat, g.d_lon, (int)n, S.stream);
+    S.launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ez_defzones.c:44-81
+int zone_extrap(const Grid &s) {
+    int extrap = 0;
+    bool through = false;
+    switch (s.grtyp) {
+        case 'N': case 'S': case '!': return 1;
+        case 'L':
+            extrap = (s.extension == 0) ? 1 : 0;
+            through = true;   // the reference's `case 'L'` has no break
+        // fallthrough
+        case '#': case 'Z': case 'Y':
+            (void)through;
+            switch (s.grref) {
+                case 'N': case 'S': extrap = 1; break;
+                case 'E': case 'L':
+                    if (!s.ax.empty() && 358.0 > (s.ax[s.ni - 1] - s.ax[0])) extrap = 1;
+                    break;
+                default: break;
+            }
+            break;
+        default: break;
+    }
+    return extrap;
+}
+
+// one (lat,lon) -> (x,y) on the device, c_gdxyfll_orig semantics; used for the pole coordinates of the zones
+int point_xy(Grid &s, float lat, float lon, float *x, float *y) {
+    float *d = (float *)S.st_misc[0].get(4 * sizeof(float));
+    if (!d) return -1;
+    float h[4] = {lat, lon, 0.f, 0.f};
+    CUDA_OK(cudaMemcpyAsync(d, h, 2 * sizeof(float), cudaMemcpyHostToDevice, S.stream));
+    ezk::ll2xy_points(to_dev(s), s.j2, d, d + 1, d + 2, d + 3, 1, S.stream);
+    S.launches++;
+    CUDA_OK(cudaMemcpyAsync(h, d, 4 * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    *x = h[2];
+    *y = h[3];
+    return 0;
+}
+
+// The gridset build: ez_calcxy (ez_calcxy.c:28) + ez_defzones (ez_defzones.c:25) for a plain source,
+// c_ezyy_calcxy (ezyy_calcxy.c:28) for a 'U' source.  Runs once per (gdout, gdin); results stay in HBM.
+Gset *ensure_gset(Grid &out, Grid &in) {
+    auto &slot = out.gsets[in.id];
+    if (!slot) {
+        slot = std::make_unique<Gset>();
+        slot->gdin = in.id;
+    }
+    Gset *gs = slot.get();
+    if (gs->built) return gs;
+    if (ensure_latlon(out) < 0) return nullptr;
+    size_t n = (size_t)out.ni * out.nj;
+    if (cudaMalloc((void **)&gs->d_x, n * sizeof(float)) != cudaSuccess || cudaMalloc((void **)&gs->d_y, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&gs->d_zb, n) != cudaSuccess) {
+        fprintf(stderr, "<ezb200> cudaMalloc failed for the gridset (%zu points): %s\n", n, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    unsigned int *d_counts = (unsigned int *)S.st_misc[1].get(8 * sizeof(unsigned int));
+    if (!d_counts) return nullptr;
+    cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned int), S.stream);
+    if (in.nsubgrids > 0) {
+        Grid *yin = grid_of(in.subgrid[0]), *yan = grid_of(in.subgrid[1]);
+        Grid *mk = yin ? grid_of(yin->mymaskgrid) : nullptr;
+        if (!yin || !yan || !mk) return nullptr;
+        if (ensure_device(*yin) < 0 || ensure_device(*yan) < 0 || ensure_device(*mk) < 0) return nullptr;
+        // the mask is produced under the caller's current polar_correction (ezyymint.c:56-64)
+        ezk::yy_calcxy(to_dev(*mk), to_dev(*yin), to_dev(*yan), S.opt.polar_correction == 1, out.d_lat, out.d_lon, gs->d_x, gs->d_y, gs->d_zb,
+                       d_counts, (int)n, S.stream);
+        S.launches++;
+        gs->yy = true;
+    } else {
+        if (in.grtyp == 'Y') {
+            fprintf(stderr, "<ezb200> 'Y' cloud as a SOURCE grid is outside the hot-path scope (SURVEY.md 8f N2)\n");
+            return nullptr;
+        }
+        if (ensure_device(in) < 0) return nullptr;
+        int extrap = zone_extrap(in);
+        float ypn = 0.f, yps = 0.f;
+        if (!extrap) {
+            if (in.grtyp == 'Z' && in.grref == 'E') {
+                ypn = in.nj + 0.5;   // ez_defzone_polenord.c:46-48, ez_defzone_polesud.c:47-49
+                yps = 0.5;
+            } else {
+                float xp;
+                if (point_xy(in, 90.0f, 0.0f, &xp, &ypn) < 0) return nullptr;
+                if (point_xy(in, -90.0f, 0.0f, &xp, &yps) < 0) return nullptr;
+            }
+        }
+        // lon is mutated in place by the A/B/L and Z-on-L coordinate routes
+        int wb = (in.grtyp == 'A' || in.grtyp == 'B' || in.grtyp == 'L' || ((in.grtyp == 'Z' || in.grtyp == '#' || in.grtyp == 'G') && in.grref == 'L'));
+        ezk::calcxy(to_dev(in), in.nj, out.d_lat, out.d_lon, wb, gs->d_x, gs->d_y, gs->d_zb, 1, extrap, ypn, yps, d_counts, (int)n, S.stream);
+        S.launches++;
+    }
+    unsigned int hc[8];
+    if (cudaMemcpyAsync(hc, d_counts, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+        cudaStreamSynchronize(S.stream) != cudaSuccess) {
+        fprintf(stderr, "<ezb200> gridset build failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    for (int k = 0; k < 6; k++) gs->counts[k] = (int)hc[k];
+    gs->built = true;
+    return gs;
+}
+
+void free_gset(Gset &gs) {
+    if (gs.d_x) cudaFree(gs.d_x);
+    if (gs.d_y) cudaFree(gs.d_y);
+    if (gs.d_zb) cudaFree(gs.d_zb);
+    gs.d_x = gs.d_y = nullptr;
+    gs.d_zb = nullptr;
+    gs.built = false;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host <-> device staging of caller arrays
+// ---------------------------------------------------------------------------------------------------
+struct Staged {
+    float *dev = nullptr;
+    float *host = nullptr;   // non-null when a copy back is due
+    size_t n = 0;
+};
+
+int stage_in(Staged &s, DevBuf &buf, const float *p, size_t n) {
+    s.n = n;
+    if (is_device_ptr(p)) { s.dev = const_cast<float *>(p); return 0; }
+    s.dev = (float *)buf.get(n * sizeof(float));
+    if (!s.dev) { fprintf(stderr, "<ezb200> cannot allocate %zu bytes of device staging\n", n * sizeof(float)); return -1; }
+    CUDA_OK(cudaMemcpyAsync(s.dev, p, n * sizeof(float), cudaMemcpyHostToDevice, S.stream));
+    return 0;
+}
+int stage_out(Staged &s, DevBuf &buf, float *p, size_t n) {
+    s.n = n;
+    if (is_device_ptr(p)) { s.dev = p; return 0; }
+    s.dev = (float *)buf.get(n * sizeof(float));
+    if (!s.dev) { fprintf(stderr, "<ezb200> cannot allocate %zu bytes of device staging\n", n * sizeof(float)); return -1; }
+    s.host = p;
+    return 0;
+}
+int finish_out(Staged &s) {
+    if (!s.host) return 0;
+    CUDA_OK(cudaMemcpyAsync(s.host, s.dev, s.n * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the scalar path on device pointers: c_ezsint_orig (ezsint.c:75-135) for nfields fields
+// ---------------------------------------------------------------------------------------------------
+InterpOpts snapshot_opts(int vector, int sym_sign) {
+    InterpOpts o;
+    o.degree = S.opt.degre_interp;
+    o.extrap = S.opt.degre_extrap;
+    o.extrap_value = S.opt.valeur_extrap;
+    o.vector = vector;
+    o.sym_sign = sym_sign;
+    o.polar = S.opt.polar_correction;
+    o.arith = S.arith;
+    return o;
+}
+
+int check_degree() {
+    int d = S.opt.degre_interp;
+    if (d == EZ_NEAREST || d == EZ_LINEAR || d == EZ_CUBIC) return 0;
+    fprintf(stderr, "<ezb200> interp_degree average/sph_average is outside the hot-path scope (SURVEY.md 8f N3)\n");
+    return -1;
+}
+
+// zin/zout are DEVICE pointers here.  Returns 0, 2 (extrapolated) or -1.
+int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign) {
+    if (check_degree() < 0) return -1;
+    Gset *gs = ensure_gset(out, in);
+    if (!gs) return -1;
+    InterpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = to_dev(in);
+    a.x = gs->d_x; a.y = gs->d_y; a.zb = gs->d_zb;
+    a.zin = d_zin; a.zout = d_zout;
+    a.in_stride = in_stride; a.out_stride = out_stride;
+    a.nfields = nfields;
+    a.npts = out.ni * out.nj;
+    a.o = snapshot_opts(vector, sym_sign);
+    int rc = 0;
+    if (gs->yy) {
+        Grid *yin = grid_of(in.subgrid[0]), *yan = grid_of(in.subgrid[1]);
+        a.src = to_dev(*yin);
+        a.src2 = to_dev(*yan);
+        a.yy = 1;
+        a.panel_stride = (long)yin->ni * yin->nj;
+        a.use_zones = 0;   // c_gdxysint calls c_gdinterp directly: no zone correction on this route (gdxysint.c:30-54)
+    } else {
+        const int *c = gs->counts;
+        bool any = (c[0] + c[1] + c[2] + c[3] + c[4]) > 0;
+        a.use_zones = (S.opt.polar_correction == 1 && any) ? 1 : 0;
+        if (a.use_zones) {
+            if (c[0] > 0) {
+                rc = 2;
+                if (S.opt.degre_extrap == EZ_ABORT) {
+                    fprintf(stderr, "<ez_corrval> There are points on the destination grid that lie outside the source grid\n");
+                    fprintf(stderr, "<ez_corrval> aborting at your request!\n\n\n");
+                    a.use_zones = 0;
+                    rc = -1;
+                }
+            }
+        }
+        if (a.use_zones) {
+            FieldScalars *fs = (FieldScalars *)S.st_fs.get((size_t)nfields * sizeof(FieldScalars));
+            unsigned int *scr = (unsigned int *)S.st_scratch.get((size_t)nfields * 2 * sizeof(unsigned int));
+            if (!fs || !scr) return -1;
+            int need_poles = (!vector) && (c[1] + c[2] + c[3] + c[4] > 0);
+            int need_minmax = (!vector) && c[0] > 0 && (S.opt.degre_extrap == EZ_MAXIMUM || S.opt.degre_extrap == EZ_MINIMUM);
+            ezk::field_scalars(a, need_poles, need_minmax, fs, scr, S.stream);
+            S.launches += need_minmax ? 3 : 1;
+            a.fs = fs;
+        }
+    }
+    S.launches += ezk::interp(a, S.stream);
+    // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged
+    if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
+        ezk::corrbgd(d_zout, out_stride, nfields, out.ni, out.nj, out.ig[0], S.stream);
+        S.launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return rc;
+}
+
+// c_ezyysint (ezyysint.c:26-242) + c_ezsint_orig, on device pointers
+int sint_any_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign) {
+    const bool yyin = in.nsubgrids > 0, yyout = out.nsubgrids > 0;
+    if (!yyin && !yyout) return sint_dev(out, in, d_zout, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
+    Grid *yin_out = yyout ? grid_of(out.subgrid[0]) : &out;
+    Grid *yan_out = yyout ? grid_of(out.subgrid[1]) : nullptr;
+    Grid *yin_in = yyin ? grid_of(in.subgrid[0]) : &in;
+    Grid *yan_in = yyin ? grid_of(in.subgrid[1]) : nullptr;
+    const long half_out = (long)yin_out->ni * yin_out->nj;
+    const long half_in = (long)yin_in->ni * yin_in->nj;
+    if (!yyin && yyout) {   // ezyysint.c:86-95
+        int r1 = sint_dev(*yin_out, in, d_zout, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
+        int r2 = sint_dev(*yan_out, in, d_zout + half_out, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
+        if (r1 < 0 || r2 < 0) return -1;
+        return (r1 == 2 || r2 == 2) ? 2 : 0;
+    }
+    // a source sub-grid IS the target (ezyysint.c:99-108)
+    if (yin_in->id == out.id) {
+        for (int f = 0; f < nfields; f++)
+            cudaMemcpyAsync(d_zout + f * out_stride, d_zin + f * in_stride, half_in * sizeof(float), cudaMemcpyDeviceToDevice, S.stream);
+        return 1;
+    }
+    if (yan_in && yan_in->id == out.id) {
+        for (int f = 0; f < nfields; f++)
+            cudaMemcpyAsync(d_zout + f * out_stride, d_zin + f * in_stride + half_in, half_in * sizeof(float), cudaMemcpyDeviceToDevice, S.stream);
+        return 1;
+    }
+    if (S.opt.use_1subgrid == 1) {   // ezyysint.c:113-138
+        if (yyout) {
+            fprintf(stderr, "<c_ezyysint> cannot use 1 subgrid to interpolate to a Yin-Yang grid  Aborting...\n");
+            return -1;
+        }
+        if (S.opt.valeur_1subgrid != yin_in->id && S.opt.valeur_1subgrid != yan_in->id) {
+            fprintf(stderr, "<c_ezyysint> define src subgridid in ezsetival(subgridid)! Aborting...\n");
+            return -1;
+        }
+        if (S.opt.valeur_1subgrid == yin_in->id) return sint_dev(*yin_out, *yin_in, d_zout, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
+        return sint_dev(*yin_out, *yan_in, d_zout, d_zin + half_in, nfields, in_stride, out_stride, vector, sym_sign);
+    }
+    // both panels, hard Yin-priority selection (ezyysint.c:142-239)
+    int rc = sint_dev(*yin_out, in, d_zout, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
+    if (rc < 0) return rc;
+    if (yyout) {
+        rc = sint_dev(*yan_out, in, d_zout + half_out, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
+        if (rc < 0) return rc;
+    }
+    return 0;
+}
+
+bool session_ok(const char *who) {
+    if (S.gdin == -1 || S.gdout == -1 || !grid_of(S.gdin) || !grid_of(S.gdout)) {
+        fprintf(stderr, "<%s> Source or target grid undefined! Aborting...\n", who);
+        return false;
+    }
+    return true;
+}
+
+int ezsint_n(float *zout, float *zin, int nfields) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    if (!session_ok("c_ezsint")) return -1;
+    if (nfields < 1) return -1;
+    Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
+    const size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
+    if (S.gdin == S.gdout) {   // ezsint.c:56-60
+        CUDA_OK(cudaMemcpyAsync(zout, zin, nin * nfields * sizeof(float), cudaMemcpyDefault, S.stream));
+        CUDA_OK(cudaStreamSynchronize(S.stream));
+        return 1;
+    }
+    Staged si, so;
+    if (stage_in(si, S.st_in[0], zin, nin * nfields) < 0) return -1;
+    if (stage_out(so, S.st_out[0], zout, nout * nfields) < 0) return -1;
+    int rc = sint_any_dev(out, in, so.dev, si.dev, nfields, (long)nin, (long)nout, 0, 1);
+    if (finish_out(so) < 0) return -1;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the vector path: c_ezuvint_orig (ezuvint.c:51-94) / c_ezyyuvint (ezyyuvint.c:28-319)
+// ---------------------------------------------------------------------------------------------------
+int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stride, int mode) {
+    if (ensure_latlon(out) < 0) return -1;
+    WindArgs w;
+    memset(&w, 0, sizeof(w));
+    if (in.nsubgrids > 0) {
+        Gset *gs = ensure_gset(out, in);
+        if (!gs) return -1;
+        w.src = to_dev(*grid_of(in.subgrid[0]));
+        w.src2 = to_dev(*grid_of(in.subgrid[1]));
+        w.yy = 1;
+        w.zb = gs->d_zb;
+    } else {
+        w.src = to_dev(in);
+    }
+    w.dst = to_dev(out);
+    w.lat = out.d_lat; w.lon = out.d_lon;
+    w.u = d_u; w.v = d_v;
+    w.stride = stride;
+    w.nfields = nfields;
+    w.npts = out.ni * out.nj;
+    w.mode = mode;
+    ezk::wind(w, S.stream);
+    S.launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+bool g_warned_polarwind = false;
+
+// uv on device pointers for one plain target (a sub-grid when the caller's target is 'U')
+int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, const float *d_vi, int nfields, long in_stride, long out_stride, int mode) {
+    const bool yyin = in.nsubgrids > 0;
+    Grid *eff_in = &in;
+    const float *ui = d_ui, *vi = d_vi;
+    if (yyin) {
+        Grid *yin_in = grid_of(in.subgrid[0]), *yan_in = grid_of(in.subgrid[1]);
+        const long half_in = (long)yin_in->ni * yin_in->nj;
+        if (yin_in->id == out.id) { eff_in = yin_in; }
+        else if (yan_in->id == out.id) { eff_in = yan_in; ui += half_in; vi += half_in; }
+        else if (S.opt.use_1subgrid == 1) {
+            if (S.opt.valeur_1subgrid == yin_in->id) eff_in = yin_in;
+            else if (S.opt.valeur_1subgrid == yan_in->id) { eff_in = yan_in; ui += half_in; vi += half_in; }
+            else {
+                fprintf(stderr, "<c_ezyyuvint> define src subgridid in ezsetival(subgridid)! Aborting...\n");
+                return -1;
+            }
+        }
+    }
+    int r1, r2;
+    if (eff_in->id == out.id) {   // c_ezsint's gdin == gdout copy, then the wind conversions still run
+        for (int f = 0; f < nfields; f++) {
+            cudaMemcpyAsync(d_uo + f * out_stride, ui + f * in_stride, (size_t)out.ni * out.nj * sizeof(float), cudaMemcpyDeviceToDevice, S.stream);
+            cudaMemcpyAsync(d_vo + f * out_stride, vi + f * in_stride, (size_t)out.ni * out.nj * sizeof(float), cudaMemcpyDeviceToDevice, S.stream);
+        }
+        r1 = r2 = 1;
+    } else {
+        r1 = sint_dev(out, *eff_in, d_uo, ui, nfields, in_stride, out_stride, 1, +1);
+        r2 = sint_dev(out, *eff_in, d_vo, vi, nfields, in_stride, out_stride, 1, -1);
+        if (r1 < 0 || r2 < 0) return -1;
+        if (eff_in->nsubgrids == 0 && S.opt.polar_correction == 1) {
+            Gset *gs = ensure_gset(out, *eff_in);
+            if (gs && (gs->counts[1] + gs->counts[2] + gs->counts[3] + gs->counts[4]) > 0 && !g_warned_polarwind) {
+                g_warned_polarwind = true;
+                fprintf(stderr, "<ezb200> warning: polar wind correction (ez_corrvec, K18) is not implemented yet; "
+                                "vector values in the two source rows next to a pole are plain interpolants\n");
+            }
+        }
+    }
+    if (wind_dev(out, *eff_in, d_uo, d_vo, nfields, out_stride, mode) < 0) return -1;
+    return (r1 == 2 || r2 == 2) ? 2 : 0;
+}
+
+int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields, int mode) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    if (!session_ok("c_ezuvint")) return -1;
+    if (nfields < 1 || check_degree() < 0) return -1;
+    Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
+    const size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
+    Staged su, sv, ou, ov;
+    if (stage_in(su, S.st_in[0], uuin, nin * nfields) < 0 || stage_in(sv, S.st_in[1], vvin, nin * nfields) < 0) return -1;
+    if (stage_out(ou, S.st_out[0], uuout, nout * nfields) < 0 || stage_out(ov, S.st_out[1], vvout, nout * nfields) < 0) return -1;
+    int rc;
+    if (out.nsubgrids > 0) {
+        if (in.nsubgrids > 0 && S.opt.use_1subgrid == 1) {
+            fprintf(stderr, "<c_ezyyuvint> cannot use 1 subgrid to interpolate to a Yin-Yang grid  Aborting...\n");
+            return -1;
+        }
+        Grid *yin_out = grid_of(out.subgrid[0]), *yan_out = grid_of(out.subgrid[1]);
+        const long half = (long)yin_out->ni * yin_out->nj;
+        int r1 = uvint_dev(*yin_out, in, ou.dev, ov.dev, su.dev, sv.dev, nfields, (long)nin, (long)nout, mode);
+        int r2 = uvint_dev(*yan_out, in, ou.dev + half, ov.dev + half, su.dev, sv.dev, nfields, (long)nin, (long)nout, mode);
+        rc = (r1 < 0 || r2 < 0) ? -1 : ((r1 == 2 || r2 == 2) ? 2 : 0);
+    } else {
+        rc = uvint_dev(out, in, ou.dev, ov.dev, su.dev, sv.dev, nfields, (long)nin, (long)nout, mode);
+    }
+    if (finish_out(ou) < 0 || finish_out(ov) < 0) return -1;
+    return rc;
+}
+
+void lower(char *dst, const char *src) {
+    size_t n = strlen(src);
+    if (n > 31) n = 31;
+    for (size_t i = 0; i < n; i++) dst[i] = (char)tolower((int)src[i]);
+    dst[n] = 0;
+}
+
+unsigned int ftn_strlen(const char *str, uint32_t maxLen) {   // src/base/ftnStrLen.c:5-19
+    if (maxLen == 0) return 0;
+    uint32_t len = maxLen - 1;
+    while (len > 0 && (str[len] == ' ' || str[len] == '\0')) len--;
+    if (str[len] != ' ' && str[len] != '\0') len++;
+    return len;
+}
+void ftn_copy(char dst[32], const char *src, int32_t l) {
+    int n = (int)ftn_strlen(src, (uint32_t)l);
+    if (n > 31) n = 31;
+    memcpy(dst, src, n);
+    dst[n] = 0;
+}
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" {
+
+const char *c_ezb200_version(void) { return "ezb200 0.1 (sm_100a)"; }
+
+int32_t c_ezb200_set_stream(void *stream) {
+    S.stream = (cudaStream_t)stream;
+    return 0;
+}
+int32_t c_ezb200_set_arith(int32_t mode) {
+    if (mode != 0 && mode != 1) return -1;
+    S.arith = mode;
+    return 0;
+}
+int32_t c_ezb200_get_arith(void) { return S.arith; }
+int64_t c_ezb200_launch_count(int32_t reset) {
+    int64_t v = S.launches;
+    if (reset) S.launches = 0;
+    return v;
+}
+int32_t c_ezb200_sync(void) {
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
+// ---- descriptors ----
+void cigaxg_(char *grtyp, float *xg1, float *xg2, float *xg3, float *xg4, const int32_t *ig1, const int32_t *ig2, const int32_t *ig3,
+             const int32_t *ig4, F2Cl l) {
+    (void)l;
+    int ig[4] = {*ig1, *ig2, *ig3, *ig4};
+    float xg[4] = {*xg1, *xg2, *xg3, *xg4};
+    if (!ezh::cigaxg(grtyp[0], xg, ig)) fprintf(stderr, "cigaxg: Bad grid pecification (TYPE)\n");
+    *xg1 = xg[0]; *xg2 = xg[1]; *xg3 = xg[2]; *xg4 = xg[3];
+}
+void cxgaig_(char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, float *xg1, float *xg2, float *xg3, float *xg4, F2Cl l) {
+    (void)l;
+    int ig[4] = {0, 0, 0, 0};
+    float xg[4] = {*xg1, *xg2, *xg3, *xg4};
+    if (!ezh::cxgaig(grtyp[0], ig, xg)) fprintf(stderr, "cxgaig: Unknown grid (TYPE)\n");
+    *ig1 = ig[0]; *ig2 = ig[1]; *ig3 = ig[2]; *ig4 = ig[3];
+}
+
+// ---- grid definition ----
+int32_t c_ezgdef_fmem(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, float *ax, float *ay) {
+    return gdef_fmem(ni, nj, grtyp, grref, ig1, ig2, ig3, ig4, ax, ay);
+}
+int32_t ezgdef_fmem_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, float *ax,
+                     float *ay, F2Cl l1, F2Cl l2) {
+    (void)l1; (void)l2;
+    char t[2] = {grtyp[0], 0}, r[2] = {grref[0], 0};
+    return c_ezgdef_fmem(*ni, *nj, t, r, *ig1, *ig2, *ig3, *ig4, ax, ay);
+}
+int32_t c_ezqkdef(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit) {
+    (void)iunit;
+    char t = grtyp[0];
+    if (t == '#' || t == 'Y' || t == 'Z' || t == 'U' || t == ' ') {   // ezgdef_ffile.c:44-50
+        fprintf(stderr, "<c_ezqkdef> grid type '%c' needs positional records from an RPN standard file; FST I/O is outside the "
+                        "hot-path scope -- define it from memory with c_ezgdef_fmem / c_ezgdef_supergrid\n", t);
+        return -1;
+    }
+    char r[2] = {' ', 0};
+    return c_ezgdef_fmem(ni, nj, grtyp, r, ig1, ig2, ig3, ig4, nullptr, nullptr);
+}
+int32_t ezqkdef_(int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, int32_t *iunit, F2Cl l) {
+    (void)l;
+    char t[2] = {grtyp[0], 0};
+    return c_ezqkdef(*ni, *nj, t, *ig1, *ig2, *ig3, *ig4, *iunit);
+}
+int32_t c_ezgdef(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, float *ax, float *ay) {
+    if (grtyp[0] == '#') {
+        fprintf(stderr, "The '#' grid type is not supported with ezgdef.\nPlease use ezgdef_ffile or ezgdef_fmem\n");
+        return -1;
+    }
+    if ((grtyp[0] == 'Y' || grtyp[0] == 'Z') && grref && (0 == strcmp(grref, "FILE") || 0 == strcmp(grref, "file"))) {
+        fprintf(stderr, "<c_ezgdef> FILE sources need FST I/O, which is outside the hot-path scope\n");
+        return -1;
+    }
+    return c_ezgdef_fmem(ni, nj, grtyp, grref, ig1, ig2, ig3, ig4, ax, ay);
+}
+int32_t ezgdef_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, float *ax, float *ay,
+                F2Cl l1, F2Cl l2) {
+    (void)l1; (void)l2;
+    char t[2] = {grtyp[0], 0}, r[2] = {grref[0], 0};
+    return c_ezgdef(*ni, *nj, t, r, *ig1, *ig2, *ig3, *ig4, ax, ay);
+}
+
+int32_t c_ezgdef_supergrid(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t vercode, int32_t nsubgrids, int32_t *subgrid) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    if (nsubgrids <= 1) {
+        fprintf(stderr, "<c_ezgdef_supergrid> nsubgrids given is less than 2! Aborting...\n");
+        return -1;
+    }
+    if (vercode != 1) {
+        fprintf(stderr, "<c_ezgdef_supergrid> invalid vercode! Aborting...\n");
+        return -1;
+    }
+    if (nsubgrids != 2 || !grid_of(subgrid[0]) || !grid_of(subgrid[1])) {
+        fprintf(stderr, "<c_ezgdef_supergrid> exactly two defined sub-grids (Yin, Yang) are supported\n");
+        return -1;
+    }
+    Grid *s0 = grid_of(subgrid[0]);
+    // identity rule for 'U' grids (ez_findgrid.c:33-46): type, ref, ig of the first sub-grid
+    for (auto &up : g_grids) {
+        Grid *g = up.get();
+        if (g && g->alive && g->nsubgrids > 0 && g->grtyp == grtyp[0] && g->grref == grref[0] && g->ni == ni && g->nj == nj &&
+            memcmp(g->ig, s0->ig, sizeof(int) * 4) == 0 && g->subgrid[0] == subgrid[0] && g->subgrid[1] == subgrid[1]) {
+            g->access_count++;
+            return g->id;
+        }
+    }
+    auto g = std::make_unique<Grid>();
+    g->grtyp = grtyp[0];
+    g->grref = grref[0];
+    g->ni = ni;
+    g->nj = nj;
+    for (int k = 0; k < 4; k++) g->ig[k] = s0->ig[k];
+    g->igref[0] = vercode;
+    g->nsubgrids = nsubgrids;
+    g->subgrid[0] = subgrid[0];
+    g->subgrid[1] = subgrid[1];
+    g->i1 = 1; g->i2 = ni; g->j1 = 1; g->j2 = nj;
+    int id = add_grid(std::move(g));
+    for (int k = 0; k < 2; k++) gdef_yymask(*grid_of(subgrid[k]));
+    return id;
+}
+int32_t ezgdef_supergrid_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *vercode, int32_t *nsubgrids, int32_t *subgrid, F2Cl l1,
+                          F2Cl l2) {
+    (void)l1; (void)l2;
+    char t[2] = {grtyp[0], 0}, r[2] = {grref[0], 0};
+    return c_ezgdef_supergrid(*ni, *nj, t, r, *vercode, *nsubgrids, subgrid);
+}
+
+int32_t c_gdrls(int32_t gdin) {   // gdrls.c:34-90
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdin);
+    if (!g) return 0;
+    if (g->access_count > 0) g->access_count--;
+    if (g->access_count == 0) {
+        for (auto &kv : g->gsets) free_gset(*kv.second);
+        g->gsets.clear();
+        for (auto &up : g_grids)   // gridsets that use this grid as their source
+            if (up && up->alive) {
+                auto it = up->gsets.find(gdin);
+                if (it != up->gsets.end()) { free_gset(*it->second); up->gsets.erase(it); }
+            }
+        float **ptrs[] = {&g->d_ax, &g->d_ay, &g->d_cx, &g->d_cy, &g->d_lat, &g->d_lon};
+        for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+        g->alive = false;
+    }
+    return 0;
+}
+int32_t gdrls_(int32_t *gdin) { return c_gdrls(*gdin); }
+
+// ---- queries ----
+int32_t c_ezgprm(int32_t gdid, char *grtyp, int32_t *ni, int32_t *nj, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    *grtyp = g->grtyp; *ni = g->ni; *nj = g->nj;
+    *ig1 = g->ig[0]; *ig2 = g->ig[1]; *ig3 = g->ig[2]; *ig4 = g->ig[3];
+    return 0;
+}
+int32_t ezgprm_(int32_t *gdid, char *grtyp, int32_t *ni, int32_t *nj, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, F2Cl l) {
+    (void)l;
+    char t[2] = {' ', 0};
+    int32_t rc = c_ezgprm(*gdid, t, ni, nj, ig1, ig2, ig3, ig4);
+    grtyp[0] = t[0];
+    return rc;
+}
+int32_t c_ezgxprm(int32_t gdid, int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, char *grref,
+                  int32_t *ig1ref, int32_t *ig2ref, int32_t *ig3ref, int32_t *ig4ref) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    *ni = g->ni; *nj = g->nj;
+    grtyp[0] = g->grtyp; grtyp[1] = 0;
+    grref[0] = g->grref; grref[1] = 0;
+    *ig1 = g->ig[0]; *ig2 = g->ig[1]; *ig3 = g->ig[2]; *ig4 = g->ig[3];
+    *ig1ref = g->igref[0]; *ig2ref = g->igref[1]; *ig3ref = g->igref[2]; *ig4ref = g->igref[3];
+    return 0;
+}
+int32_t ezgxprm_(int32_t *gdid, int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, char *grref,
+                 int32_t *ig1ref, int32_t *ig2ref, int32_t *ig3ref, int32_t *ig4ref, F2Cl l1, F2Cl l2) {
+    (void)l1; (void)l2;
+    char t[2] = {' ', 0}, r[2] = {' ', 0};
+    int32_t rc = c_ezgxprm(*gdid, ni, nj, t, ig1, ig2, ig3, ig4, r, ig1ref, ig2ref, ig3ref, ig4ref);
+    grtyp[0] = t[0];
+    grref[0] = r[0];
+    return rc;
+}
+int32_t c_ezget_nsubgrids(int32_t gdid) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    return g->nsubgrids == 0 ? 1 : g->nsubgrids;
+}
+int32_t ezget_nsubgrids_(int32_t *gdid) { return c_ezget_nsubgrids(*gdid); }
+int32_t c_ezget_subgridids(int32_t gdid, int32_t *subgrid) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    if (g->nsubgrids == 0) { *subgrid = gdid; return 1; }
+    for (int i = 0; i < g->nsubgrids; i++) subgrid[i] = g->subgrid[i];
+    return g->nsubgrids;
+}
+int32_t ezget_subgridids_(int32_t *gdid, int32_t *subgrid) { return c_ezget_subgridids(*gdid, subgrid); }
+
+int32_t c_gdll(int32_t gdid, float *lat, float *lon) {   // gdll.c:25-73
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    if (g->nsubgrids > 0) {
+        Grid *a = grid_of(g->subgrid[0]);
+        size_t half = (size_t)a->ni * a->nj;
+        if (c_gdll(g->subgrid[0], lat, lon) < 0) return -1;
+        return c_gdll(g->subgrid[1], lat + half, lon + half);
+    }
+    if (ensure_latlon(*g) < 0) return -1;
+    size_t n = (size_t)g->ni * g->nj;
+    CUDA_OK(cudaMemcpyAsync(lat, g->d_lat, n * sizeof(float), cudaMemcpyDefault, S.stream));
+    CUDA_OK(cudaMemcpyAsync(lon, g->d_lon, n * sizeof(float), cudaMemcpyDefault, S.stream));
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+int32_t gdll_(int32_t *gdid, float *lat, float *lon) { return c_gdll(*gdid, lat, lon); }
+
+// c_gdxyfll for plain grids (gdxyfll.c:29-129; the 'U' selection logic of :190-243 is a "next" row, N1)
+int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int32_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g || n < 0) return -1;
+    if (g->nsubgrids > 0 || g->grtyp == 'Y') {
+        fprintf(stderr, "<c_gdxyfll> 'U' and 'Y' grids are not supported by this entry point yet\n");
+        return -1;
+    }
+    if (n == 0) return 0;
+    if (ensure_device(*g) < 0) return -1;
+    Staged sla, slo, sx, sy;
+    if (stage_in(sla, S.st_in[0], lat, n) < 0 || stage_in(slo, S.st_in[1], lon, n) < 0) return -1;
+    if (stage_out(sx, S.st_out[0], x, n) < 0 || stage_out(sy, S.st_out[1], y, n) < 0) return -1;
+    ezk::ll2xy_points(to_dev(*g), g->j2, sla.dev, slo.dev, sx.dev, sy.dev, n, S.stream);
+    S.launches++;
+    if (finish_out(sx) < 0 || finish_out(sy) < 0) return -1;
+    return 0;
+}
+int32_t gdxyfll_(int32_t *gdid, float *x, float *y, float *lat, float *lon, int32_t *n) { return c_gdxyfll(*gdid, x, y, lat, lon, *n); }
+
+// c_gdxysval (gdxysval.c:50-116): interpolate at caller-supplied x,y, no zone correction
+int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdin);
+    if (!g || n < 0 || check_degree() < 0) return -1;
+    if (g->grtyp == 'Y') return -1;
+    if (n == 0) return 0;
+    Grid *yin = g->nsubgrids > 0 ? grid_of(g->subgrid[0]) : g;
+    Grid *yan = g->nsubgrids > 0 ? grid_of(g->subgrid[1]) : nullptr;
+    if (ensure_device(*yin) < 0 || (yan && ensure_device(*yan) < 0)) return -1;
+    size_t nin = (size_t)g->ni * g->nj;
+    Staged sz, sx, sy, so;
+    if (stage_in(sz, S.st_in[0], zin, nin) < 0 || stage_in(sx, S.st_in[1], x, n) < 0 || stage_in(sy, S.st_misc[2], y, n) < 0) return -1;
+    if (stage_out(so, S.st_out[0], zout, n) < 0) return -1;
+    InterpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = to_dev(*yin);
+    a.x = sx.dev; a.y = sy.dev;
+    a.zin = sz.dev; a.zout = so.dev;
+    a.in_stride = (long)nin; a.out_stride = n;
+    a.nfields = 1; a.npts = n;
+    a.o = snapshot_opts(0, 1);
+    if (yan) {
+        fprintf(stderr, "<c_gdxysval> 'U' sources are not supported by this entry point yet\n");
+        return -1;
+    }
+    S.launches += ezk::interp(a, S.stream);
+    if (finish_out(so) < 0) return -1;
+    return 0;
+}
+int32_t gdxysval_(int32_t *gdin, float *zout, float *zin, float *x, float *y, int32_t *n) { return c_gdxysval(*gdin, zout, zin, x, y, *n); }
+
+int c_gdsetmask(int gdid, int *mask) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    if (g->nsubgrids > 0) { fprintf(stderr, "<gdsetmask> This operation is not supported for 'U' grids.\n"); return -1; }
+    g->mask.assign(mask, mask + (size_t)g->ni * g->nj);
+    g->has_mask = true;
+    return 0;
+}
+int gdsetmask_(int *gdid, int *mask) { return c_gdsetmask(*gdid, mask); }
+int c_gdgetmask(int gdid, int *mask) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    if (g->nsubgrids > 0) { fprintf(stderr, "<gdgetmask> This operation is not supported for 'U' grids.\n"); return -1; }
+    if (!g->has_mask) return -1;
+    memcpy(mask, g->mask.data(), g->mask.size() * sizeof(int));
+    return 0;
+}
+int gdgetmask_(int *gdid, int *mask) { return c_gdgetmask(*gdid, mask); }
+
+// ---- gridset selection ----
+int32_t c_ezdefset(int32_t gdout, int32_t gdin) {   // ezdefset.c:38-170 ; the x/y arrays are built lazily by the first compute call
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    if (gdout == -1 && gdin != -1) gdout = gdin;
+    if (!grid_of(gdin) || !grid_of(gdout)) {
+        fprintf(stderr, "<c_ezdefset> undefined grid id (gdout=%d gdin=%d)\n", gdout, gdin);
+        return -1;
+    }
+    S.gdin = gdin;
+    S.gdout = gdout;
+    if (gdin != gdout) {
+        auto &slot = grid_of(gdout)->gsets[gdin];
+        if (!slot) {
+            slot = std::make_unique<Gset>();
+            slot->gdin = gdin;
+        }
+    }
+    return 1;
+}
+int32_t ezdefset_(int32_t *gdout, int32_t *gdin) { return c_ezdefset(*gdout, *gdin); }
+int32_t c_ezgetgdin(void) { return S.gdin; }
+int32_t c_ezgetgdout(void) {
+    if (S.gdout == -1 && S.gdin != -1) S.gdout = S.gdin;
+    return S.gdout;
+}
+
+// ---- hot path ----
+int32_t c_ezsint(float *zout, float *zin) { return ezsint_n(zout, zin, 1); }
+int32_t ezsint_(float *zout, float *zin) { return c_ezsint(zout, zin); }
+int32_t c_ezsint_batch(float *zout, float *zin, int32_t nfields) { return ezsint_n(zout, zin, nfields); }
+int32_t c_ezuvint(float *uuout, float *vvout, float *uuin, float *vvin) { return ezuvint_n(uuout, vvout, uuin, vvin, 1, 0); }
+int32_t ezuvint_(float *uuout, float *vvout, float *uuin, float *vvin) { return c_ezuvint(uuout, vvout, uuin, vvin); }
+int32_t c_ezuvint_batch(float *uuout, float *vvout, float *uuin, float *vvin, int32_t nfields) {
+    return ezuvint_n(uuout, vvout, uuin, vvin, nfields, 0);
+}
+int32_t c_ezwdint(float *spdout, float *wdout, float *uuin, float *vvin) { return ezuvint_n(spdout, wdout, uuin, vvin, 1, 1); }
+int32_t ezwdint_(float *spdout, float *wdout, float *uuin, float *vvin) { return c_ezwdint(spdout, wdout, uuin, vvin); }
+
+int c_ezsint_mask(int *mask_out, int *mask_in) {   // ez_mask.c:184-223
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    if (!session_ok("ezsint_mask")) return -1;
+    Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
+    if (in.nsubgrids > 0 || out.nsubgrids > 0) {
+        fprintf(stderr, "<ezsint_mask> This operation is not supported for 'U' grids.\n");
+        return -1;
+    }
+    if (in.id == out.id || in.grtyp == 'Y') return -1;
+    Gset *gs = ensure_gset(out, in);
+    if (!gs) return -1;
+    size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
+    bool din = is_device_ptr(mask_in), dout = is_device_ptr(mask_out);
+    int *d_in = din ? mask_in : (int *)S.st_in[0].get(nin * sizeof(int));
+    int *d_out = dout ? mask_out : (int *)S.st_out[0].get(nout * sizeof(int));
+    if (!d_in || !d_out) return -1;
+    if (!din) CUDA_OK(cudaMemcpyAsync(d_in, mask_in, nin * sizeof(int), cudaMemcpyHostToDevice, S.stream));
+    ezk::mask_transfer(gs->d_x, gs->d_y, d_in, d_out, out.ni, out.nj, in.ni, in.nj, S.opt.cld_interp_alg == EZ_LINEAR, S.stream);
+    S.launches++;
+    if (!dout) {
+        CUDA_OK(cudaMemcpyAsync(mask_out, d_out, nout * sizeof(int), cudaMemcpyDeviceToHost, S.stream));
+        CUDA_OK(cudaStreamSynchronize(S.stream));
+    }
+    return 0;
+}
+int ezsint_mask_(int *mask_out, int *mask_in) { return c_ezsint_mask(mask_out, mask_in); }
+
+int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, uint8_t *zonebits, int32_t *counts) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *o = grid_of(gdout), *i = grid_of(gdin);
+    if (!o || !i || o->nsubgrids > 0) return -1;
+    Gset *gs = ensure_gset(*o, *i);
+    if (!gs) return -1;
+    size_t n = (size_t)o->ni * o->nj;
+    if (x) CUDA_OK(cudaMemcpyAsync(x, gs->d_x, n * sizeof(float), cudaMemcpyDefault, S.stream));
+    if (y) CUDA_OK(cudaMemcpyAsync(y, gs->d_y, n * sizeof(float), cudaMemcpyDefault, S.stream));
+    if (zonebits) CUDA_OK(cudaMemcpyAsync(zonebits, gs->d_zb, n, cudaMemcpyDefault, S.stream));
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    if (counts) for (int k = 0; k < 6; k++) counts[k] = gs->counts[k];
+    return 0;
+}
+
+// ---- options (ezsetopt.c:59-215, ezsetval.c:86-148, ezgetopt.c:53-234, ezgetval.c:55-120) ----
+int32_t c_ezsetopt(char *option, char *value) {
+    char o[32], v[32];
+    lower(o, option);
+    lower(v, value);
+    if (!strcmp(o, "correction_polaire")) strcpy(o, "polar_correction");
+    if (!strcmp(o, "degre_interp")) strcpy(o, "interp_degree");
+    if (!strcmp(o, "degre_extrap")) strcpy(o, "extrap_degree");
+    if (!strcmp(o, "use_1sousgrille")) strcpy(o, "use_1subgrid");
+    if (!strcmp(v, "oui")) strcpy(v, "yes");
+    if (!strcmp(v, "ouiouioui")) strcpy(v, "yesyesyes");
+    if (!strcmp(v, "non")) strcpy(v, "no");
+    if (!strcmp(v, "voisin")) strcpy(v, "nearest");
+    if (!strcmp(v, "lineair") || !strcmp(v, "lineaire")) strcpy(v, "linear");
+    if (!strcmp(v, "cubique")) strcpy(v, "cubic");
+    if (!strcmp(v, "neutre")) strcpy(v, "neutral");
+    if (!strcmp(v, "valeur")) strcpy(v, "value");
+    int option_ok = 0, value_ok = 0;
+    Options &g = S.opt;
+    if (!strcmp(o, "use_1subgrid")) {
+        option_ok = value_ok = 1;
+        if (!strcmp(v, "yes")) g.use_1subgrid = 1;
+        else if (!strcmp(v, "no")) g.use_1subgrid = 0;
+        else value_ok = 0;
+    }
+    if (!strcmp(o, "verbose")) {
+        option_ok = value_ok = 1;
+        if (!strcmp(v, "yes")) g.verbose = 1;
+        else if (!strcmp(v, "yesyesyes")) g.verbose = 2;
+        else if (!strcmp(v, "no")) g.verbose = 0;
+        else value_ok = 0;
+    }
+    if (!strcmp(o, "polar_correction")) {
+        option_ok = value_ok = 1;
+        if (!strcmp(v, "yes")) g.polar_correction = 1;
+        else if (!strcmp(v, "no")) g.polar_correction = 0;
+        else value_ok = 0;
+    }
+    if (!strcmp(o, "interp_degree")) {
+        option_ok = value_ok = 1;
+        if (!strcmp(v, "nearest")) g.degre_interp = 0;
+        else if (!strcmp(v, "linear")) g.degre_interp = 1;
+        else if (!strcmp(v, "cubic")) g.degre_interp = 3;
+        else if (!strcmp(v, "average")) g.degre_interp = 4;
+        else if (!strcmp(v, "sph_average")) g.degre_interp = 5;
+        else value_ok = 0;
+    }
+    if (!strcmp(o, "extrap_degree")) {
+        option_ok = value_ok = 1;
+        if (!strcmp(v, "neutral")) g.degre_extrap = g.degre_interp;
+        else if (!strcmp(v, "nearest")) g.degre_extrap = 0;
+        else if (!strcmp(v, "linear")) g.degre_extrap = 1;
+        else if (!strcmp(v, "cubic")) g.degre_extrap = 3;
+        else if (!strcmp(v, "maximum")) g.degre_extrap = EZ_MAXIMUM;
+        else if (!strcmp(v, "minimum")) g.degre_extrap = EZ_MINIMUM;
+        else if (!strcmp(v, "value")) g.degre_extrap = EZ_VALUE;
+        else if (!strcmp(v, "abort")) g.degre_extrap = EZ_ABORT;
+        else value_ok = 0;
+    }
+    if (!strcmp(o, "cloud_interp_alg")) {
+        if (!strcmp(v, "linear")) { value_ok = option_ok = 1; g.cld_interp_alg = EZ_LINEAR; }
+        if (!strcmp(v, "distance")) { value_ok = option_ok = 1; g.cld_interp_alg = 4; }
+    }
+    if (value_ok + option_ok != 2) {
+        if (!option_ok) fprintf(stderr, "ezsetopt : option not recognized : %s\n", option);
+        if (!value_ok) fprintf(stderr, "ezsetopt : value not recognized : %s\n", value);
+        return -1;
+    }
+    return 0;
+}
+int32_t ezsetopt_(char *option, char *value, F2Cl lo, F2Cl lv) {
+    char o[32], v[32];
+    ftn_copy(o, option, lo);
+    ftn_copy(v, value, lv);
+    return c_ezsetopt(o, v);
+}
+int32_t c_ezsetval(char *option, float fvalue) {
+    char o[32];
+    lower(o, option);
+    if (!strcmp(o, "extrap_value")) S.opt.valeur_extrap = fvalue;
+    if (!strcmp(o, "missing_gridpt_distance")) S.opt.msg_gridpt_dist = fvalue;
+    if (!strcmp(o, "missing_distance_threshold")) S.opt.msg_dist_thresh = fvalue;
+    return 0;
+}
+int32_t ezsetval_(char *option, float *fvalue, F2Cl l) {
+    char o[32];
+    ftn_copy(o, option, l);
+    return c_ezsetval(o, *fvalue);
+}
+int32_t c_ezsetival(char *option, int32_t ivalue) {
+    char o[32];
+    lower(o, option);
+    if (!strcmp(o, "weight_number")) S.opt.wgt_num = ivalue;
+    if (!strcmp(o, "missing_points_tolerance")) S.opt.msg_pt_tol = ivalue;
+    if (!strcmp(o, "subgridid")) S.opt.valeur_1subgrid = ivalue;
+    return 0;
+}
+int32_t ezsetival_(char *option, int32_t *ivalue, F2Cl l) {
+    char o[32];
+    ftn_copy(o, option, l);
+    return c_ezsetival(o, *ivalue);
+}
+int32_t c_ezgetopt(char *option, char *value) {
+    char o[32];
+    lower(o, option);
+    const Options &g = S.opt;
+    auto deg = [](int d, bool fr, bool ex) -> const char * {
+        switch (d) {
+            case 0: return fr ? "voisin" : "nearest";
+            case 1: return fr ? "lineaire" : "linear";
+            case 3: return fr ? "cubique" : "cubic";
+            default: break;
+        }
+        if (ex) {
+            if (d == EZ_MAXIMUM) return "maximum";
+            if (d == EZ_MINIMUM) return "minimum";
+            if (d == EZ_VALUE) return fr ? "valeur" : "value";
+            if (d == EZ_ABORT) return "abort";
+        }
+        return fr ? "erreur" : "error";
+    };
+    if (!strcmp(o, "verbose")) strcpy(value, g.verbose == 1 ? "yes" : (g.verbose == 2 ? "yesyesyes" : "no"));
+    if (!strcmp(o, "use_1subgrid")) strcpy(value, g.use_1subgrid == 1 ? "yes" : "no");
+    if (!strcmp(o, "polar_correction")) strcpy(value, g.polar_correction == 1 ? "yes" : "no");
+    if (!strcmp(o, "interp_degree")) strcpy(value, deg(g.degre_interp, false, false));
+    if (!strcmp(o, "degre_interp")) strcpy(value, deg(g.degre_interp, true, false));
+    if (!strcmp(o, "extrap_degree")) strcpy(value, deg(g.degre_extrap, false, true));
+    if (!strcmp(o, "degre_extrap")) strcpy(value, deg(g.degre_extrap, true, true));
+    if (!strcmp(o, "cloud_interp_alg")) strcpy(value, g.cld_interp_alg == EZ_LINEAR ? "linear" : "distance");
+    return 0;
+}
+int32_t ezgetopt_(char *option, char *value, F2Cl lo, F2Cl lv) {
+    char o[32], v[32];
+    v[0] = 0;
+    ftn_copy(o, option, lo);
+    int32_t rc = c_ezgetopt(o, v);
+    int len = (int)strlen(v);
+    if (len > lv) len = lv;
+    memcpy(value, v, len);
+    if (len < lv) value[len] = 0;
+    return rc;
+}
+int32_t c_ezgetval(char *option, float *value) {
+    char o[32];
+    lower(o, option);
+    if (!strcmp(o, "extrap_value")) *value = S.opt.valeur_extrap;
+    if (!strcmp(o, "missing_distance_threshold")) *value = S.opt.msg_dist_thresh;
+    if (!strcmp(o, "weight_number")) *value = (float)S.opt.wgt_num;
+    if (!strcmp(o, "missing_points_tolerance")) *value = (float)S.opt.msg_pt_tol;
+    return 0;
+}
+int32_t ezgetval_(char *option, float *value, F2Cl l) {
+    char o[32];
+    ftn_copy(o, option, l);
+    return c_ezgetval(o, value);
+}
+int32_t c_ezgetival(char *option, int32_t *value) {
+    char o[32];
+    lower(o, option);
+    if (!strcmp(o, "subgridid")) *value = S.opt.valeur_1subgrid;
+    if (!strcmp(o, "weight_number")) *value = S.opt.wgt_num;
+    if (!strcmp(o, "missing_points_tolerance")) *value = S.opt.msg_pt_tol;
+    return 0;
+}
+int32_t ezgetival_(char *option, int32_t *value, F2Cl l) {
+    char o[32];
+    ftn_copy(o, option, l);
+    return c_ezgetival(o, value);
+}
+
+}  // extern "C"

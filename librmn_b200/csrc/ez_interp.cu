@@ -1,0 +1,609 @@
+// librmn_b200/csrc/ez_interp.cu -- gather-interpolation kernels (K0-K10, K19 of SURVEY.md 2.3), sm_100a.
+//
+// Layout: one thread per target point, fields/levels looped INSIDE the thread so that x, y and the zone
+// byte (9 B/point) are read once per batch and the stencil indices/weights are computed once and reused
+// for every level.  Consecutive threads own consecutive target points: the output store of each level is
+// one fully coalesced 128-B line per warp, and the source gathers of neighbouring points fall in the same
+// few 128-B lines (L1-resident; the whole source level set of one wave of CTAs sits in the 126 MB L2).
+// Zone handling (DEHORS / AU_NORD / AU_SUD / POLE_*, ez_corrval.c) is fused in as a per-point class, so
+// there is no second scatter pass and no compaction.
+//
+// Arithmetic modes (InterpOpts.arith):
+//   0  "reference order": every fp32/fp64 operation in the order the Fortran leaves perform it
+//      (ez_rgdint_*.inc, ez_irgdint_*.inc) -- used for bit-parity tests;
+//   1  "weight form": the same interpolant written as sum_a sum_b wx_a wy_b z_ab with the 4+4 (or 2+2)
+//      weights evaluated once per point in fp64 and applied with fp64 FMAs per level.
+// Compiled with -fmad=false; the weight form uses explicit fma().
+#include <cuda_runtime.h>
+#include <math.h>
+#include "ez_kernels.h"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ int f_ifix(float x) { return (int)x; }
+__device__ __forceinline__ int f_nint(float x) { return (int)lroundf(x); }
+
+// ---------------------------------------------------------------------------------------------------
+// field access
+// ---------------------------------------------------------------------------------------------------
+// Logical z(i, j), i in 1..ni, j in j1..j2 of the (possibly y-inverted, possibly hemispherically mirrored)
+// source field.  Folds permut() (ezsint.c:100-106) and ez_xpngdag2/ez_xpngdb2 (K11) into index math.
+struct FieldFetch {
+    const float *__restrict__ z;
+    int ni, nj, j1, xpn, yinv;
+    float sgn;
+    __device__ __forceinline__ float operator()(int i, int j) const {
+        if (xpn == XPN_NONE && !yinv) return __ldg(z + (long)(j - j1) * ni + (i - 1));
+        int jj = j;
+        float s = 1.0f;
+        switch (xpn) {
+            case XPN_AG_NORTH: if (j < 1) { jj = 1 - j; s = sgn; } break;
+            case XPN_AG_SOUTH: if (j > nj) { jj = 2 * nj - j + 1; s = sgn; } break;
+            case XPN_B_NORTH:  if (j < 1) { jj = 2 - j; s = sgn; } break;
+            case XPN_B_SOUTH:  if (j > nj) { jj = 2 * nj - j; s = sgn; } break;
+            default: break;
+        }
+        if (yinv) jj = nj + 1 - jj;
+        return s * __ldg(z + (long)(jj - 1) * ni + (i - 1));
+    }
+};
+
+// temp(ni,4) of ez_fillnpole / ez_fillspole, never materialised: three source rows + a constant pole row.
+// jbase = the j index of strip row 0 ; pole_row = 3 (north) or 0 (south) ; jsrc0 = source j of the first data row.
+struct StripFetch {
+    FieldFetch f;
+    int jbase, pole_row, jsrc0;
+    float poleval;
+    __device__ __forceinline__ float operator()(int i, int j) const {
+        int r = j - jbase;
+        if (r == pole_row) return poleval;
+        return f(i, jsrc0 + (pole_row == 0 ? r - 1 : r));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// reference-order evaluators
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double zlin(double a, double b, double dx) { return a + (b - a) * dx; }
+
+// cubic8.cdk:3 with the default-real literals rounded to fp32
+__device__ __forceinline__ double cubic(double z1, double z2, double z3, double z4, double dx) {
+    const double c6 = (double)0.1666666666666f, c3 = (double)0.3333333333333f, h = 0.5;
+    return ((((z4 - z1) * c6 + h * (z2 - z3)) * dx + h * (z1 + z3) - z2) * dx + z3 - c6 * z4 - h * z2 - c3 * z1) * dx + z2;
+}
+
+// ez_rgdint_0.inc:27-32
+template <class F>
+__device__ __forceinline__ float rgd0(const F &z, int ni, int j1, int j2, float px, float py) {
+    int i = min(ni, max(1, f_nint(px)));
+    int j = min(j2, max(j1, f_nint(py)));
+    return z(i, j);
+}
+
+// ez_rgdint_1_nw.inc:30-41 (wrap < 0) and ez_rgdint_1_w.inc:31-48 (wrap >= 0)
+template <class F>
+__device__ __forceinline__ float rgd1(const F &z, int ni, int j1, int j2, int wrap, float px, float py) {
+    int i, ip1;
+    if (wrap < 0) {
+        i = min(ni - 1, max(1, f_ifix(px)));
+        ip1 = i + 1;
+    } else {
+        int limite = ni + 2 - wrap;
+        i = min(ni - 2 + wrap, max(1, f_ifix(px)));
+        ip1 = i + 1;
+        if (wrap > 0 && i == (ni - 2 + wrap)) ip1 = (limite + i + 1) % limite;
+    }
+    int j = min(j2 - 1, max(j1, f_ifix(py)));
+    double dx = (double)(px - (float)i);
+    double dy = (double)(py - (float)j);
+    double y2 = zlin((double)z(i, j), (double)z(ip1, j), dx);
+    double y3 = zlin((double)z(i, j + 1), (double)z(ip1, j + 1), dx);
+    return (float)zlin(y2, y3, dy);
+}
+
+// column indices of ez_rgdint_3_nw.inc:61 (mode 0), ez_rgdint_3_w.inc:72-93 (mode 1), ez_rgdint_3_wnnc.inc:73-93 (mode 2)
+__device__ __forceinline__ void rgd3_cols(int mode, int ni, int wrap, float px, int &i, int &im1, int &ip1, int &ip2) {
+    if (mode == 0) {
+        i = min(ni - 2, max(2, f_ifix(px)));
+        im1 = i - 1; ip1 = i + 1; ip2 = i + 2;
+        return;
+    }
+    int limite = ni + 2 - wrap;
+    i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
+    bool wrapped = (mode == 1) ? (wrap > 0) : ((wrap > 0 && i <= 1) || i >= (ni - 1));
+    if (wrapped) {
+        im1 = (limite + i - 1) % limite;
+        ip1 = (limite + i + 1) % limite;
+        ip2 = (limite + i + 2) % limite;
+        if (im1 == 0) im1 = ni;
+        if (i == 0) i = ni;
+        if (ip1 == 0) ip1 = ni;
+        if (ip2 == 0) ip2 = ni;
+        if (wrap == 1) {
+            if (ip2 == ni) ip2 = 2;
+            if (im1 == ni) im1 = ni - 1;
+        }
+    } else {
+        im1 = i - 1; ip1 = i + 1; ip2 = i + 2;
+    }
+}
+
+template <class F>
+__device__ __forceinline__ float rgd3(const F &z, int mode, int ni, int j1, int j2, int wrap, float px, float py) {
+    int i, im1, ip1, ip2;
+    rgd3_cols(mode, ni, wrap, px, i, im1, ip1, ip2);
+    int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
+    double dx = (double)(px - (float)i);
+    double dy = (double)(py - (float)j);
+    double y1 = cubic(z(im1, j - 1), z(i, j - 1), z(ip1, j - 1), z(ip2, j - 1), dx);
+    double y2 = cubic(z(im1, j), z(i, j), z(ip1, j), z(ip2, j), dx);
+    double y3 = cubic(z(im1, j + 1), z(i, j + 1), z(ip1, j + 1), z(ip2, j + 1), dx);
+    double y4 = cubic(z(im1, j + 2), z(i, j + 2), z(ip1, j + 2), z(ip2, j + 2), dx);
+    return (float)cubic(y1, y2, y3, y4, dy);
+}
+
+// ez_irgdint_1_nw.inc:31-47 ; ay is 1-based over nj
+template <class F>
+__device__ __forceinline__ float irgd1_nw(const F &z, const float *__restrict__ ax, const float *__restrict__ ay, int ni, int nj, float px, float py) {
+    int i = min(ni - 1, max(1, f_ifix(px)));
+    int j = min(nj - 1, max(1, f_ifix(py)));
+    float axi = __ldg(ax + i - 1), axi1 = __ldg(ax + i), ayj = __ldg(ay + j - 1), ayj1 = __ldg(ay + j);
+    double x1 = axi, x2 = axi1;
+    double x = (double)axi + (x2 - x1) * (double)(px - (float)i);
+    double y = (double)(ayj + (ayj1 - ayj) * (py - (float)j));
+    double dx = (x - x1) / (x2 - x1);
+    double dy = (y - (double)ayj) / (double)(ayj1 - ayj);
+    double y1 = zlin((double)z(i, j), (double)z(i + 1, j), dx);
+    double y2 = zlin((double)z(i, j + 1), (double)z(i + 1, j + 1), dx);
+    return (float)zlin(y1, y2, dy);
+}
+
+// ez_irgdint_1_w.inc:31-61 ; ay(j1:j2)
+template <class F>
+__device__ __forceinline__ float irgd1_w(const F &z, const float *__restrict__ ax, const float *__restrict__ ay, int ni, int j1, int j2, int wrap,
+                                         float px, float py) {
+    int limite = ni + 2 - wrap;
+    int i = min(ni - 2 + wrap, max(1, f_ifix(px)));
+    int j = min(j2 - 1, max(j1 + 1, f_ifix(py)));
+    if (j < 0) j = j - 1;
+    int ip1 = i + 1;
+    double x1 = __ldg(ax + i - 1), x2 = 0.0;
+    if (ip1 <= ni) x2 = __ldg(ax + ip1 - 1);
+    if (wrap > 0 && i == (ni - 2 + wrap)) {
+        ip1 = (limite + i + 1) % limite;
+        x2 = (double)(__ldg(ax + 1) + __ldg(ax + ni - 1));
+    }
+    float ayj = __ldg(ay + (j - j1)), ayj1 = __ldg(ay + (j + 1 - j1));
+    double x = x1 + (x2 - x1) * (double)(px - (float)i);
+    double y = (double)(ayj + (ayj1 - ayj) * (py - (float)j));
+    double dx = (x - x1) / (x2 - x1);
+    double dy = (y - (double)ayj) / (double)(ayj1 - ayj);
+    double y1 = zlin((double)z(i, j), (double)z(ip1, j), dx);
+    double y2 = zlin((double)z(i, j + 1), (double)z(ip1, j + 1), dx);
+    return (float)zlin(y1, y2, dy);
+}
+
+// Newton divided-difference statement functions, ez_irgdint_3_nw.inc:84-87
+__device__ __forceinline__ double nfa(double a1, double a2, double a3, double a4, double x, double x1, double x2, double x3) {
+    return a1 + (x - x1) * (a2 + (x - x2) * (a3 + a4 * (x - x3)));
+}
+__device__ __forceinline__ double nfa2(double c1, double a1, double a2) { return c1 * (a2 - a1); }
+__device__ __forceinline__ double nfa3(double c1, double c2, double c3, double a1, double a2, double a3) {
+    return c2 * (c3 * (a3 - a2) - c1 * (a2 - a1));
+}
+__device__ __forceinline__ double nfa4(double c1, double c2, double c3, double c4, double c5, double c6, double a1, double a2, double a3, double a4) {
+    return c4 * (c5 * (c6 * (a4 - a3) - c3 * (a3 - a2)) - c2 * (c3 * (a3 - a2) - c1 * (a2 - a1)));
+}
+
+// One Newton pass over 4 samples.  R4 = true rounds every statement-function result to fp32, as
+// ez_irgdint_3_nw.inc:32 declares fa..fa4 REAL; false keeps fp64 (ez_irgdint_3_w.inc:78, _wnnc:28).
+template <bool R4>
+__device__ __forceinline__ double newton4(const double c[6], double z1, double z2, double z3, double z4, double x, double x1, double x2, double x3) {
+    double a2 = nfa2(c[0], z1, z2);
+    double a3 = nfa3(c[0], c[1], c[2], z1, z2, z3);
+    double a4 = nfa4(c[0], c[1], c[2], c[3], c[4], c[5], z1, z2, z3, z4);
+    if (R4) { a2 = (double)(float)a2; a3 = (double)(float)a3; a4 = (double)(float)a4; }
+    double r = nfa(z1, a2, a3, a4, x, x1, x2, x3);
+    if (R4) r = (double)(float)r;
+    return r;
+}
+
+// ez_irgdint_3_nw.inc:89-165 ; ax(i1:i2), ay(j1:j2), cx(i1:i2,6), cy(j1:j2,6)
+template <class F>
+__device__ __forceinline__ float irgd3_nw(const F &z, const GridDev &g, float px, float py) {
+    const int i1 = g.i1, i2 = g.i2, j1 = g.j1, j2 = g.j2;
+    const int nx = i2 - i1 + 1, ny = j2 - j1 + 1;
+    int i = min(i2 - 2, max(i1 + 1, f_ifix(px)));
+    int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
+    const float *ax = g.ax - i1, *ay = g.ay - j1;
+    float axm = __ldg(ax + i - 1), ax0 = __ldg(ax + i), axp = __ldg(ax + i + 1);
+    float aym = __ldg(ay + j - 1), ay0 = __ldg(ay + j), ayp = __ldg(ay + j + 1);
+    double x = (double)(ax0 + (axp - ax0) * (px - (float)i));
+    double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
+    double cx[6], cy[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        cx[k] = (double)__ldg(g.cx + (long)k * nx + (i - i1));
+        cy[k] = (double)__ldg(g.cy + (long)k * ny + (j - j1));
+    }
+    double b[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int jj = j - 1 + r;
+        b[r] = newton4<true>(cx, z(i - 1, jj), z(i, jj), z(i + 1, jj), z(i + 2, jj), x, axm, ax0, axp);
+    }
+    double b2 = (double)(float)nfa2(cy[0], b[0], b[1]);
+    double b3 = (double)(float)nfa3(cy[0], cy[1], cy[2], b[0], b[1], b[2]);
+    double b4 = (double)(float)nfa4(cy[0], cy[1], cy[2], cy[3], cy[4], cy[5], b[0], b[1], b[2], b[3]);
+    return (float)nfa(b[0], b2, b3, b4, y, aym, ay0, ayp);
+}
+
+// seam logic of ez_irgdint_3_w.inc:97-160 (nnc = false) / ez_irgdint_3_wnnc.inc (nnc = true, iplus2 = 1 at wrap 1, i = ni-1)
+__device__ __forceinline__ void seam_x(int wrap, int ni, const float *__restrict__ ax, int i, bool nnc, int &im1, int &ip1, int &ip2,
+                                       float &x1, float &x2, float &x3, float &x4) {
+#define AX(k) __ldg(ax + (k)-1)
+    im1 = i - 1; ip1 = i + 1; ip2 = i + 2;
+    if (wrap == 1 && (i <= 1 || i >= (ni - wrap))) {
+        if (i == 1) {
+            im1 = ni - 1; ip1 = 2; ip2 = 3;
+            x1 = AX(ni - 1) - 360.0f; x2 = AX(1); x3 = AX(2); x4 = AX(3);
+        }
+        if (i == (ni - 1)) {
+            im1 = ni - 2; ip1 = ni; ip2 = nnc ? 1 : 2;
+            x1 = AX(ni - 2); x2 = AX(ni - 1); x3 = AX(ni); x4 = AX(2) + 360.0f;
+        }
+    } else if (wrap == 2 && (i <= 1 || i > (ni - wrap))) {
+        if (i == 1) {
+            im1 = ni; ip1 = 2; ip2 = 3;
+            x1 = AX(ni) - 360.0f; x2 = AX(1); x3 = AX(2); x4 = AX(3);
+        }
+        if (i == (ni - 1)) {
+            im1 = ni - 2; ip1 = ni; ip2 = 1;
+            x1 = AX(ni - 2); x2 = AX(ni - 1); x3 = AX(ni); x4 = AX(1) + 360.0f;
+        }
+        if (i == ni) {
+            im1 = ni - 1; ip1 = 1; ip2 = 2;
+            x1 = AX(ni - 1); x2 = AX(ni); x3 = AX(1) + 360.0f; x4 = AX(2) + 360.0f;
+        }
+    } else {
+        x1 = AX(im1); x2 = AX(i); x3 = AX(ip1); x4 = AX(ip2);
+    }
+#undef AX
+}
+
+// ez_irgdint_3_w.inc:93-229 ; cx(ni,6), ay/cy over j1:j2
+template <class F>
+__device__ __forceinline__ float irgd3_w(const F &z, const GridDev &g, float px, float py) {
+    const int ni = g.ni, j1 = g.j1, j2 = g.j2, wrap = g.ext;
+    const int ny = j2 - j1 + 1;
+    int i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
+    int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
+    int im1, ip1, ip2;
+    float x1 = 0.f, x2 = 0.f, x3 = 0.f, x4 = 0.f;
+    seam_x(wrap, ni, g.ax, i, false, im1, ip1, ip2, x1, x2, x3, x4);
+    const float *ay = g.ay - j1;
+    float aym = __ldg(ay + j - 1), ay0 = __ldg(ay + j), ayp = __ldg(ay + j + 1);
+    double x = (double)(x2 + (x3 - x2) * (px - (float)i));
+    double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
+    double cx[6], cy[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        cx[k] = (double)__ldg(g.cx + (long)k * ni + (i - 1));
+        cy[k] = (double)__ldg(g.cy + (long)k * ny + (j - j1));
+    }
+    double b[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int jj = j - 1 + r;
+        b[r] = newton4<false>(cx, z(im1, jj), z(i, jj), z(ip1, jj), z(ip2, jj), x, x1, x2, x3);
+    }
+    double b2 = nfa2(cy[0], b[0], b[1]);
+    double b3 = nfa3(cy[0], cy[1], cy[2], b[0], b[1], b[2]);
+    double b4 = nfa4(cy[0], cy[1], cy[2], cy[3], cy[4], cy[5], b[0], b[1], b[2], b[3]);
+    return (float)nfa(b[0], b2, b3, b4, y, aym, ay0, ayp);
+}
+
+// ez_irgdint_3_wnnc.inc:93-243 ; coefficients on the fly, 4-row strip z(ni, j1:j2), ay4 = ay(j1:j2)
+template <class F>
+__device__ __forceinline__ float irgd3_wnnc(const F &z, const float *__restrict__ ax, const float ay4[4], int ni, int j1, int j2, int wrap,
+                                            float px, float py) {
+    int i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
+    int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
+    int im1, ip1, ip2;
+    float fx1 = 0.f, fx2 = 0.f, fx3 = 0.f, fx4 = 0.f;
+    seam_x(wrap, ni, ax, i, true, im1, ip1, ip2, fx1, fx2, fx3, fx4);
+    double x1 = fx1, x2 = fx2, x3 = fx3, x4 = fx4;
+    float ay0 = ay4[j - j1], ayp = ay4[j + 1 - j1];
+    double x = x2 + (x3 - x2) * (double)(px - (float)i);
+    double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
+    double cx[6] = {1.0 / (x2 - x1), 1.0 / (x3 - x1), 1.0 / (x3 - x2), 1.0 / (x4 - x1), 1.0 / (x4 - x2), 1.0 / (x4 - x3)};
+    double y1 = ay4[j - 1 - j1], y2 = ay0, y3 = ayp, y4 = ay4[j + 2 - j1];
+    double b[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int jj = j - 1 + r;
+        b[r] = newton4<false>(cx, z(im1, jj), z(i, jj), z(ip1, jj), z(ip2, jj), x, x1, x2, x3);
+    }
+    double cy[6] = {1.0 / (y2 - y1), 1.0 / (y3 - y1), 1.0 / (y3 - y2), 1.0 / (y4 - y1), 1.0 / (y4 - y2), 1.0 / (y4 - y3)};
+    double b2 = nfa2(cy[0], b[0], b[1]);
+    double b3 = nfa3(cy[0], cy[1], cy[2], b[0], b[1], b[2]);
+    double b4 = nfa4(cy[0], cy[1], cy[2], cy[3], cy[4], cy[5], b[0], b[1], b[2], b[3]);
+    return (float)nfa(b[0], b2, b3, b4, y, y1, y2, y3);
+}
+
+// c_gdinterp's dispatch (gdinterp.c:133-281) for one point, reference-order arithmetic
+template <class F>
+__device__ __forceinline__ float interp_point(const F &z, const GridDev &g, int degree, float px, float py) {
+    const bool irregular = (g.grtyp == '#' || g.grtyp == 'Z' || g.grtyp == 'G');
+    if (degree == EZ_NEAREST) return rgd0(z, g.ni, g.j1, g.j2, px, py);
+    if (irregular) {
+        if (degree == EZ_LINEAR) {
+            if (g.ext == 0) return irgd1_nw(z, g.ax, g.ay, g.ni, g.nj, px, py);
+            return irgd1_w(z, g.ax, g.ay, g.ni, g.j1, g.j2, g.ext, px, py);
+        }
+        if (g.ext == 0) return irgd3_nw(z, g, px, py);
+        return irgd3_w(z, g, px, py);
+    }
+    if (degree == EZ_LINEAR) {
+        if (g.ext == 2) return rgd1(z, g.ni, g.j1, g.j2, 2, px, py);
+        return rgd1(z, g.ni, g.j1, g.j2, -1, px, py);
+    }
+    if (g.ext == 0) return rgd3(z, 0, g.ni, g.j1, g.j2, 0, px, py);
+    return rgd3(z, 1, g.ni, g.j1, g.j2, g.ext, px, py);
+}
+
+__device__ __forceinline__ FieldFetch make_fetch(const GridDev &g, const float *z, int sym_sign) {
+    FieldFetch f;
+    f.z = z; f.ni = g.ni; f.nj = g.nj; f.j1 = g.j1; f.xpn = g.xpn; f.yinv = g.yinv;
+    f.sgn = (float)sym_sign;
+    return f;
+}
+
+// ez_corrval_aunord.c:39-112 / ez_corrval_ausud.c:46-129 for one point
+__device__ __noinline__ float polar_point(const FieldFetch &ff, const GridDev &g, int degree, bool north, float poleval, float px, float py) {
+    StripFetch s;
+    s.f = ff;
+    s.poleval = poleval;
+    const bool irr = (g.grtyp == 'Z' || g.grtyp == 'G');   // ('E' has no axes in the reference: regular strip)
+    if (north) {
+        int j1s = g.j2 - 2, j2s = j1s + 3;
+        s.pole_row = 3; s.jsrc0 = g.j2 - 2;
+        if (degree == EZ_CUBIC) {
+            s.jbase = j1s;
+            if (irr) {
+                float ay4[4];
+                const float *ay = g.ay;   // C 0-based indices on the raw axis, ez_corrval_aunord.c:61-77
+                if (__ldg(ay + g.j2 - 1) == 90.0f) {
+                    ay4[0] = __ldg(ay + g.j2 - 4); ay4[1] = __ldg(ay + g.j2 - 3); ay4[2] = __ldg(ay + g.j2 - 2); ay4[3] = __ldg(ay + g.j2 - 1);
+                } else {
+                    ay4[0] = __ldg(ay + g.j2 - 3); ay4[1] = __ldg(ay + g.j2 - 2); ay4[2] = __ldg(ay + g.j2 - 1); ay4[3] = 90.0f;
+                }
+                return irgd3_wnnc(s, g.ax, ay4, g.ni, j1s, j2s, g.ext, px, py);
+            }
+            return rgd3(s, 2, g.ni, j1s, j2s, g.ext, px, py);
+        }
+        // linear / nearest: strip indexed 1..4 with y shifted by (j2-3) in double, ez_corrval_aunord.c:88-105
+        s.jbase = 1;
+        float ty = (float)((double)py - (1.0 * (double)(g.j2 - 3)));
+        if (degree == EZ_LINEAR) return rgd1(s, g.ni, 1, 4, g.ext, px, ty);
+        return rgd0(s, g.ni, 1, 4, px, ty);
+    }
+    int j1s = g.j1 - 1, j2s = j1s + 3;
+    s.pole_row = 0; s.jsrc0 = g.j1; s.jbase = j1s;
+    if (degree == EZ_CUBIC) {
+        if (irr) {
+            float ay4[4];
+            const float *ay = g.ay;       // ez_corrval_ausud.c:66-92
+            if (__ldg(ay + g.j1 - 1) == -90.0f) {
+                ay4[0] = __ldg(ay + 0); ay4[1] = __ldg(ay + 1); ay4[2] = __ldg(ay + 2); ay4[3] = __ldg(ay + 3);
+            } else {
+                ay4[0] = -90.0f; ay4[1] = __ldg(ay + 0); ay4[2] = __ldg(ay + 1); ay4[3] = __ldg(ay + 2);
+            }
+            return irgd3_wnnc(s, g.ax, ay4, g.ni, j1s, j2s, g.ext, px, py);
+        }
+        return rgd3(s, 2, g.ni, j1s, j2s, g.ext, px, py);
+    }
+    if (degree == EZ_LINEAR) return rgd1(s, g.ni, j1s, j2s, g.ext, px, py);
+    return rgd0(s, g.ni, j1s, j2s, px, py);
+}
+
+// everything ez_corrval.c:54-143 does to one point carrying zone bits
+__device__ __noinline__ float zone_point(const FieldFetch &ff, const GridDev &g, const InterpOpts &o, uint8_t bits, const FieldScalars *fs,
+                                         int f, float px, float py, float normal) {
+    float v = normal;
+    if (bits & ZB_DEHORS) {
+        if (o.extrap >= EZ_MAXIMUM)
+            v = (o.vector || !fs) ? 0.0f : fs[f].fudge;
+        else
+            v = interp_point(ff, g, o.extrap, px, py);
+    }
+    if (o.vector) return v;
+    if (bits & ZB_AU_NORD) v = polar_point(ff, g, o.degree, true, fs[f].pole_n, px, py);
+    if (bits & ZB_AU_SUD) v = polar_point(ff, g, o.degree, false, fs[f].pole_s, px, py);
+    if (bits & ZB_POLE_NORD) v = fs[f].pole_n;
+    if (bits & ZB_POLE_SUD) v = fs[f].pole_s;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the interpolation kernel: generic, reference-order arithmetic
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_interp_ref(InterpArgs a) {
+    int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= a.npts) return;
+    const float px = a.x[n], py = a.y[n];
+    const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
+    const bool yang = a.yy && (bits & ZB_YANG);
+    const GridDev &g = yang ? a.src2 : a.src;
+    const float *zbase = a.zin + (yang ? a.panel_stride : 0);
+    const uint8_t zbits = a.use_zones ? (uint8_t)(bits & 0x1f) : (uint8_t)0;
+    for (int f = 0; f < a.nfields; f++) {
+        FieldFetch ff = make_fetch(g, zbase + (long)f * a.in_stride, a.o.sym_sign);
+        float v = interp_point(ff, g, a.o.degree, px, py);
+        if (zbits) v = zone_point(ff, g, a.o, zbits, a.fs, f, px, py, v);
+        a.zout[(long)f * a.out_stride + n] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K10 pre-pass: per-field scalars
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int f2ord(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void k_minmax_init(unsigned int *scratch, int nfields) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nfields) {
+        scratch[2 * f] = 0xffffffffu;   // min
+        scratch[2 * f + 1] = 0u;        // max
+    }
+}
+
+// ez_aminmax.inc:26-27 over the logical (expanded) field z(ni, j1:j2); grid = (blocks, nfields)
+__global__ void __launch_bounds__(TPB) k_minmax(InterpArgs a, unsigned int *scratch) {
+    const int f = blockIdx.y;
+    const GridDev &g = a.src;
+    FieldFetch ff = make_fetch(g, a.zin + (long)f * a.in_stride, a.o.sym_sign);
+    const long total = (long)g.ni * (g.j2 - g.j1 + 1);
+    float mn = INFINITY, mx = -INFINITY;
+    for (long k = (long)blockIdx.x * TPB + threadIdx.x; k < total; k += (long)gridDim.x * TPB) {
+        int i = (int)(k % g.ni) + 1, j = (int)(k / g.ni) + g.j1;
+        float v = ff(i, j);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(scratch + 2 * f, f2ord(mn));
+        atomicMax(scratch + 2 * f + 1, f2ord(mx));
+    }
+}
+
+// ez_calcpoleval.inc:30-45: strictly sequential fp32 accumulation (one thread per field and pole) so the
+// pole value is bit-identical to the reference's; plus the DEHORS fudge value of ez_corrval.c:62-91.
+__global__ void k_field_scalars(InterpArgs a, int need_poles, int need_minmax, FieldScalars *fs, const unsigned int *scratch) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = t >> 1, which = t & 1;
+    if (f >= a.nfields) return;
+    const GridDev &g = a.src;
+    if (need_poles) {
+        FieldFetch ff = make_fetch(g, a.zin + (long)f * a.in_stride, a.o.sym_sign);
+        int jrow = which ? g.j1 : g.j2;   // north pole uses the last row, south the first (ez_corrval.c:133-140)
+        float p = 0.0f;
+        if (g.grtyp == 'Z' && g.grref == 'E') {
+            for (int i = 1; i <= g.ni - 1; i++) p = p + ff(i, jrow) * (__ldg(g.ax + i) - __ldg(g.ax + i - 1));
+            float span = __ldg(g.ax + g.ni - 1) - __ldg(g.ax);
+            if (span != 0.0f) p = p / span;
+        } else {
+            for (int i = 1; i <= g.ni; i++) p = p + ff(i, jrow);
+            p = p / (1.0f * (float)g.ni);
+        }
+        if (which) fs[f].pole_s = p; else fs[f].pole_n = p;
+    }
+    if (which == 0) {
+        float fudge = 0.0f;
+        if (need_minmax) {
+            float valmin = ord2f(scratch[2 * f]), valmax = ord2f(scratch[2 * f + 1]);
+            if (a.o.extrap == EZ_MAXIMUM) fudge = (float)((double)valmax + 0.05 * (double)(valmax - valmin));
+            if (a.o.extrap == EZ_MINIMUM) fudge = (float)((double)valmin - 0.05 * (double)(valmax - valmin));
+        }
+        if (a.o.extrap == EZ_VALUE) fudge = a.o.extrap_value;
+        fs[f].fudge = fudge;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K19 integer mask transfer, ezget_mask_zones.inc:75-103
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_mask(const float *__restrict__ x, const float *__restrict__ y, const int *__restrict__ mask_in,
+                                              int *__restrict__ mask_out, int ni_out, int nj_out, int ni_in, int nj_in, int linear) {
+    int k = blockIdx.x * TPB + threadIdx.x;
+    int npts = ni_out * nj_out;
+    if (k >= npts) return;
+    int io = k % ni_out, jo = k / ni_out;
+    float px = x[k], py = y[k];
+    int ix = (int)px, iy = (int)py, nix = f_nint(px), niy = f_nint(py);
+    const long nin = (long)ni_in * nj_in;
+    int m = 1;
+    if (ix < 1 || ix > ni_in || iy < 1 || iy > nj_in) {
+        m = 0;
+    } else {
+        long q = (long)(niy - 1) * ni_in + (nix - 1);
+        if (q >= 0 && q < nin && mask_in[q] == 0) m = 0;
+    }
+    // second pass only touches i < ni_out, j < nj_out (ezget_mask_zones.inc:91-92); neighbours are plain
+    // column-major address arithmetic, storage outside the array is treated as non-zero
+    if (linear && m == 1 && io < ni_out - 1 && jo < nj_out - 1) {
+        long q1 = (long)(iy - 1) * ni_in + ix, q2 = (long)iy * ni_in + (ix - 1), q3 = (long)iy * ni_in + ix;
+        if ((q1 < nin && mask_in[q1] == 0) || (q2 < nin && mask_in[q2] == 0) || (q3 < nin && mask_in[q3] == 0)) m = 0;
+    }
+    mask_out[k] = m;
+}
+
+// ez_corrbgd.inc:29-52: one thread per (field, pole row), sequential fp32 sum
+__global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = t >> 1, which = t & 1;
+    if (f >= nfields) return;
+    bool doit = which == 0 ? (hem == 0 || hem == 2) : (hem == 0 || hem == 1);
+    if (!doit) return;
+    float *row = zout + (long)f * stride + (which == 0 ? 0 : (long)(nj - 1) * ni);
+    float somme = 0.f;
+    for (int i = 0; i < ni; i++) somme = somme + row[i];
+    float moyenne = somme / ((float)ni * 1.0f);
+    for (int i = 0; i < ni; i++) row[i] = moyenne;
+}
+
+}  // namespace
+
+#include "ez_interp_fast.cuh"
+
+namespace ezk {
+
+void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s) {
+    if (a.nfields <= 0) return;
+    if (need_minmax) {
+        k_minmax_init<<<(a.nfields + 127) / 128, 128, 0, s>>>(scratch, a.nfields);
+        long total = (long)a.src.ni * (a.src.j2 - a.src.j1 + 1);
+        int bx = (int)((total + (long)TPB * 8 - 1) / ((long)TPB * 8));
+        if (bx < 1) bx = 1;
+        if (bx > 592) bx = 592;   // 4 CTAs x 148 SMs per field is plenty for a streaming min/max
+        dim3 grid(bx, a.nfields);
+        k_minmax<<<grid, TPB, 0, s>>>(a, scratch);
+    }
+    int nt = 2 * a.nfields;
+    k_field_scalars<<<(nt + 63) / 64, 64, 0, s>>>(a, need_poles, need_minmax, fs, scratch);
+}
+
+int interp(const InterpArgs &a, cudaStream_t s) {
+    if (a.npts <= 0 || a.nfields <= 0) return 0;
+    if (a.o.arith == 1 && launch_fast(a, s)) return 1;
+    int nb = (a.npts + TPB - 1) / TPB;
+    k_interp_ref<<<nb, TPB, 0, s>>>(a);
+    return 1;
+}
+
+void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,
+                   int linear, cudaStream_t s) {
+    int npts = ni_out * nj_out;
+    if (npts <= 0) return;
+    k_mask<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(x, y, mask_in, mask_out, ni_out, nj_out, ni_in, nj_in, linear);
+}
+
+void corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem, cudaStream_t s) {
+    int nt = 2 * nfields;
+    if (nt <= 0) return;
+    k_corrbgd<<<(nt + 63) / 64, 64, 0, s>>>(zout, stride, nfields, ni, nj, hem);
+}
+
+}  // namespace ezk

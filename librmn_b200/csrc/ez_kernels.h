@@ -1,0 +1,59 @@
+// librmn_b200/csrc/ez_kernels.h -- host-side launchers of the CUDA kernels (internal interface between the
+// host logic in ez_host.cu and the kernel translation units).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ez_types.h"
+
+// Everything a gather-interpolation launch needs, by value.
+struct InterpArgs {
+    GridDev src;            // source grid (Yin panel when the source is a 'U' supergrid)
+    GridDev src2;           // Yang panel (only read when yy != 0)
+    int yy;                 // source is Yin-Yang: ZB_YANG in zb picks src2 and adds panel_stride to the field base
+    long panel_stride;      // ni*nj of one panel
+    const float *x, *y;     // device, npts each (fractional 1-based source coordinates)
+    const uint8_t *zb;      // device zone/panel bits, or nullptr
+    int use_zones;          // apply zone handling (polar_correction on, zones built)
+    const float *zin;       // device source fields
+    float *zout;            // device target fields
+    long in_stride, out_stride;   // elements between consecutive fields
+    int nfields;
+    int npts;
+    InterpOpts o;
+    const FieldScalars *fs; // device per-field scalars (pole means, fudge) or nullptr
+};
+
+struct WindArgs {
+    GridDev src;            // grid whose frame (u,v) are currently expressed in
+    GridDev src2;           // Yang panel
+    int yy;
+    GridDev dst;            // grid whose frame they must be expressed in
+    const float *lat, *lon; // device lat/lon of the target points
+    const uint8_t *zb;      // panel bits (yy) or nullptr
+    float *u, *v;           // device, in place
+    long stride;
+    int nfields;
+    int npts;
+    int mode;               // 0: uv(src frame) -> uv(dst frame) ; 1: -> (speed,direction) only ; 2: (speed,direction) -> uv(dst)
+};
+
+namespace ezk {
+void calclatlon(const GridDev &g, float *lat, float *lon, int npts, cudaStream_t s);
+void calcxy(const GridDev &src, int njs, const float *lat, float *lon, int writeback_lon, float *x, float *y, uint8_t *zb,
+            int zones_enabled, int extrap, float ypolenord, float ypolesud, unsigned int *counts, int npts, cudaStream_t s);
+void yy_calcxy(const GridDev &maskgrid, const GridDev &yin, const GridDev &yan, int use_mask, const float *lat, const float *lon,
+               float *x, float *y, uint8_t *zb, unsigned int *counts, int npts, cudaStream_t s);
+void ll2xy_points(const GridDev &g, int njs, const float *lat, const float *lon, float *x, float *y, int npts, cudaStream_t s);
+
+// K10 pre-pass: per-field pole-row means (sequential fp32 sums, bit-faithful to ez_calcpoleval) and min/max.
+void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s);
+// K0-K9: the gather-interpolation kernel.  Returns the number of kernel launches issued.
+int interp(const InterpArgs &a, cudaStream_t s);
+// K19 integer mask transfer
+void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,
+                   int linear, cudaStream_t s);
+// K17 wind rotation
+void wind(const WindArgs &a, cudaStream_t s);
+// B-grid pole-row averaging, ez_corrbgd.inc:29-52
+void corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem, cudaStream_t s);
+}  // namespace ezk

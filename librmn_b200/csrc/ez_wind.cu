@@ -1,0 +1,151 @@
+// librmn_b200/csrc/ez_wind.cu -- wind-vector rotation (K17 of SURVEY.md 2.3), sm_100a.
+//
+// The reference turns grid-frame (u,v) into (speed, meteorological direction) on the SOURCE grid's frame
+// (c_gdwdfuv_orig, gdwdfuv.c:43-97) and then into (u,v) on the TARGET grid's frame (c_gduvfwd_orig,
+// gduvfwd.c:43-93) in about ten full passes over the output with four temporaries malloc'd per call
+// (ezuvint.c:81-86, ez_llwfgfw.c:58-69).  Here both stages are fused into one pass: one thread per target
+// point, (u,v) of every field updated in place, the per-point trigonometry (rotated lat/lon, sines and
+// cosines) evaluated once and reused for all fields.  Compiled with -fmad=false.
+#include "ez_devmath.cuh"
+#include "ez_kernels.h"
+
+namespace {
+
+constexpr int TPB = 256;
+
+struct Rot {          // per-point constants of a rotated ('E' / ref 'E') frame
+    double sa, ca, sc, cc;   // sin/cos of DAR*lon_rot, DAR*lat_rot   (ez_uvacart on the rotated frame)
+    double st, ct, se, ce;   // sin/cos of DAR*lon_true, DAR*lat_true (ez_cartauv on the true frame)
+};
+
+__device__ __forceinline__ bool is_rotated(const GridDev &g) {
+    if (g.grtyp == 'E') return true;
+    if ((g.grtyp == '#' || g.grtyp == 'Y' || g.grtyp == 'Z') && g.grref == 'E') return true;
+    return false;
+}
+// grid-type letter and dgrw that ez_llwfgdw / ez_gdwfllw see (gdwdfuv.c:80-95, gduvfwd.c:81-92)
+__device__ __forceinline__ char frame_type(const GridDev &g) {
+    if (g.grtyp == '#' || g.grtyp == 'Y' || g.grtyp == 'Z') return g.grref;
+    return g.grtyp;
+}
+__device__ __forceinline__ float frame_dgrw(const GridDev &g) {
+    if (g.grtyp == '#' || g.grtyp == 'Y' || g.grtyp == 'Z') return g.xgref[3];
+    return g.xg[3];
+}
+
+__device__ __forceinline__ float wrapdir(float d) { return fmodf(fmodf(d, 360.0f) + 360.0f, 360.0f); }
+
+// ez_llwfgdw.inc:49-164 for one point; t = frame letter
+__device__ __forceinline__ void llwfgdw1(char t, float dgrw, float xlon, float &z1, float &z2) {
+    float uu = z1, vv = z2;
+    if (!(t == 'N' || t == 'S' || t == 'A' || t == 'B' || t == 'G' || t == 'L')) return;   // "bad grid type": untouched
+    float spd0 = sqrtf(uu * uu + vv * vv), dir0;
+    if (spd0 == 0.0f) {
+        dir0 = 0.0f;
+    } else if (uu == 0.0f) {
+        if (t == 'N') dir0 = (vv >= 0.0f) ? xlon + dgrw - 90.0f : xlon + dgrw + 90.0f;
+        else if (t == 'S') dir0 = (vv >= 0.0f) ? 90.0f - xlon + dgrw : 270.0f - xlon + dgrw;
+        else dir0 = (vv >= 0.0f) ? 180.0f : 0.0f;
+    } else {
+        float at = EZ_RDTODG_F * ez_atan2f(vv, uu);
+        if (t == 'N') dir0 = xlon + dgrw - at;
+        else if (t == 'S') dir0 = 180.0f - xlon + dgrw - at;
+        else dir0 = 270.0f - at;
+    }
+    z1 = spd0;
+    z2 = wrapdir(dir0);
+}
+
+// ez_gdwfllw.inc:89-133 for one point
+__device__ __forceinline__ void gdwfllw1(char t, float dgrw, float xlon, float &z1, float &z2) {
+    float psi;
+    if (t == 'N') psi = xlon + dgrw - z2;
+    else if (t == 'S') psi = 180.0f - xlon + dgrw - z2;
+    else if (t == 'A' || t == 'B' || t == 'G' || t == 'L') psi = 270.0f - z2;
+    else return;
+    float u = ez_cosf(psi * EZ_DGTORD_F) * z1;
+    float v = ez_sinf(psi * EZ_DGTORD_F) * z1;
+    z1 = u;
+    z2 = v;
+}
+
+__device__ __forceinline__ Rot make_rot(const GridDev &g, float lat, float lon) {
+    Rot r;
+    float lonr, latr;
+    ez_rotate_ll(g.r, lon, lat, lonr, latr);     // ez_gfxyfll: true -> rotated
+    const double dar = (double)ez_dar();         // DAR = ACOS(-1.)/180. evaluated in fp32, ez_uvacart.inc:45
+    sincos(dar * (double)lonr, &r.sa, &r.ca);
+    sincos(dar * (double)latr, &r.sc, &r.cc);
+    sincos(dar * (double)lon, &r.st, &r.ct);
+    sincos(dar * (double)lat, &r.se, &r.ce);
+    return r;
+}
+
+// ez_uvacart.inc:49-58 ; (lon,lat) sines/cosines passed in
+__device__ __forceinline__ void uvacart1(float u, float v, double a, double b, double c, double d, float &x0, float &x1, float &x2) {
+    x0 = (float)(-((double)u * a) - ((double)v * b * c));
+    x1 = (float)(((double)u * b) - ((double)v * a * c));
+    x2 = (float)((double)v * d);
+}
+// ez_cartauv.inc:48-58
+__device__ __forceinline__ void cartauv1(float c0, float c1, float c2, double a, double b, double e, double f, float &u, float &v) {
+    u = (float)(((double)c1 * a) - ((double)c0 * b));
+    double c = ((double)c0 * a) + ((double)c1 * b);
+    double d = sqrt(c * c + (double)(c2 * c2));
+    v = (float)copysign(fabs(d), ((double)c2 * e) - (c * f));
+}
+
+__global__ void __launch_bounds__(TPB) k_wind(WindArgs a) {
+    int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= a.npts) return;
+    const float lat = a.lat[n], lon = a.lon[n];
+    const bool yang = a.yy && a.zb && (a.zb[n] & ZB_YANG);
+    const GridDev &gs = yang ? a.src2 : a.src;
+    const GridDev &gd = a.dst;
+    const bool do1 = (a.mode != 2), do2 = (a.mode != 1);
+    const bool rot_s = do1 && is_rotated(gs), rot_d = do2 && is_rotated(gd);
+    Rot rs, rd;
+    if (rot_s) rs = make_rot(gs, lat, lon);
+    if (rot_d) rd = make_rot(gd, lat, lon);
+    const char ts = frame_type(gs), td = frame_type(gd);
+    const float dgs = frame_dgrw(gs), dgd = frame_dgrw(gd);
+    for (int f = 0; f < a.nfields; f++) {
+        long k = (long)f * a.stride + n;
+        float u = a.u[k], v = a.v[k];
+        if (do1) {
+            if (rot_s) {
+                // c_ezllwfgfw, ez_llwfgfw.c:62-69: rotated-frame winds -> true-frame winds -> (spd, dir)
+                float x0, x1, x2, c0, c1, c2;
+                uvacart1(u, v, rs.sa, rs.ca, rs.sc, rs.cc, x0, x1, x2);
+                ez_mxm3(gs.ri, x0, x1, x2, c0, c1, c2);
+                cartauv1(c0, c1, c2, rs.ct, rs.st, rs.ce, rs.se, u, v);
+                llwfgdw1('L', 0.f, lon, u, v);
+            } else {
+                llwfgdw1(ts, dgs, lon, u, v);
+            }
+        }
+        if (do2) {
+            if (rot_d) {
+                // c_ezgfwfllw, ez_gfwfllw.c:66-72: (spd, dir) -> true-frame winds -> rotated-frame winds
+                float x0, x1, x2, c0, c1, c2;
+                gdwfllw1('L', 0.f, lon, u, v);
+                uvacart1(u, v, rd.st, rd.ct, rd.se, rd.ce, x0, x1, x2);
+                ez_mxm3(gd.r, x0, x1, x2, c0, c1, c2);
+                cartauv1(c0, c1, c2, rd.ca, rd.sa, rd.cc, rd.sc, u, v);
+            } else {
+                gdwfllw1(td, dgd, lon, u, v);
+            }
+        }
+        a.u[k] = u;
+        a.v[k] = v;
+    }
+}
+
+}  // namespace
+
+namespace ezk {
+void wind(const WindArgs &a, cudaStream_t s) {
+    if (a.npts <= 0 || a.nfields <= 0) return;
+    k_wind<<<(a.npts + TPB - 1) / TPB, TPB, 0, s>>>(a);
+}
+}  // namespace ezk
