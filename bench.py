@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the EZ interpolator hot path (BASELINE.json: output points/s of
+c_ezsint / c_ezuvint, and achieved HBM GB/s against the measured peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c5|c1|c3|c4]
+
+A "step" is ONE pass of the hot path over one batch of synthetic fields: c_ezsint_batch(zout, zin, L) for
+the configured workload (default = BASELINE.json configs[1]: GEM Yin-Yang 'U' -> 0.1 deg 'L', cubic, 80 levels).
+  value : output points/s with source and target fields resident in HBM (device pointers through the C ABI)
+  e2e   : the same call with HOST (pinned) buffers -- host->device and device->host copies inside the timed region
+N > 1 (torchrun, one rank per GPU): levels are partitioned, every rank holds a replicated gridset and its own
+L levels (weak scaling, no data-path collective); time = max over ranks.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libezref.so: its unmodified
+src/interp/*.c + our restatement of its Fortran leaves) on the host cores, on a bounded sample of the same
+workload.  The oracle is never on the product path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libezref.so")
+
+
+# --------------------------------------------------------------------------------------------------
+def workload(lib, name):
+    from librmn_b200 import configs
+    if name == "c2":
+        return configs.c2(lib, 0.15, 0.1, "cubic"), 80, "c_ezsint cubic, GEM Yin-Yang 'U' (2 x 1841x641 Z/E panels) -> 'L' 0.1deg 3600x1801, 80 levels"
+    if name == "c5":
+        return configs.c5(lib, 0.15, 0.1, "cubic"), 80, "c_ezsint cubic, global 'Z' 0.15deg 2401x1200 -> 'L' 0.1deg 3600x1801, 80 levels per GPU"
+    if name == "c1":
+        return configs.c1(lib, 2048, "linear"), 1, "c_ezsint bilinear, 'L' 720x361 -> 'N' 2048x2048, 1 field"
+    if name == "c3":
+        return configs.c3(lib, 1, "cubic"), 1, "c_ezuvint cubic, rotated 'Z' 2576x1456 -> 'L' 3200x1600, 1 (u,v) pair"
+    if name == "c4":
+        return configs.c4(lib, 1600, 800, 1_000_000, "linear"), 16, "c_ezsint linear, 'G' 1600x800 -> 'Y' 1M points, 16 fields"
+    raise SystemExit("unknown workload %s" % name)
+
+
+def algorithmic_bytes(case, nfields):
+    """F*(4 N_src + 4 N_out) + 9 N_out per batch (x, y, zone byte read once per batch)."""
+    comps = 2 if case.vector else 1
+    return comps * nfields * 4 * (case.n_src + case.n_out) + 9 * case.n_out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(name, nfields_sample, nthreads, steps, warmup):
+    """Times oracle/_ref (the reference's C + restated Fortran leaves) on host cores. Returns (pts/s, ms/step, case)."""
+    import ctypes as C
+    from librmn_b200 import EzLib
+    if not os.path.exists(REF_SO):
+        raise SystemExit("oracle/_ref/libezref.so missing: run `make -C oracle` where /root/reference exists")
+    R = EzLib(REF_SO)
+    case, _, desc = workload(R, name)
+    case.defset()
+    nin, nout = case.n_src, case.n_out
+    zin = np.stack([case.source(k).ravel() for k in range(nfields_sample)])
+    zout = np.zeros((nfields_sample, nout), np.float32)
+    vin = vout = None
+    if case.vector:
+        uv = [case.source_uv(k) for k in range(nfields_sample)]
+        zin = np.stack([u.ravel() for u, _ in uv])
+        vin = np.stack([v.ravel() for _, v in uv])
+        vout = np.zeros_like(zout)
+    # one warm single-threaded call builds the gridset (the reference's registry is not thread safe while building)
+    if case.vector:
+        R.ezuvint(zout[0], vout[0], zin[0], vin[0])
+    else:
+        R.ezsint(zout[0], zin[0])
+    fn = R.lib.ezref_mt
+    fn.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]
+    interp = case.opts.get("interp_degree", "cubic").encode()
+    extrap = case.opts.get("extrap_degree", "maximum").encode()
+
+    def step():
+        return fn(case.gdout, case.gdin, zout.ctypes.data, zin.ctypes.data, vout.ctypes.data if vout is not None else None,
+                  vin.ctypes.data if vin is not None else None, nin, nout, nfields_sample, nthreads, interp, extrap)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return nout * nfields_sample / dt, dt * 1e3, case, desc
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--levels", type=int, default=0, help="override the number of fields per step")
+    ap.add_argument("--cpu-sample-levels", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--arith", type=int, default=1)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "output_points_per_second"
+    unit = "points/s"
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 5))
+        warm = max(1, min(args.warmup, 2))
+        v, ms, case, desc = cpu_reference_run(args.workload, args.cpu_sample_levels, cores, steps, warm)
+        sample = "%d of the workload's levels per step, %d threads each calling c_ezdefset+c_ezsint on its own levels" % (args.cpu_sample_levels, cores)
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-on-f32", "data": "synthetic",
+                "config": {"workload": desc, "sample": sample},
+                "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import librmn_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libezb200.so has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = librmn_b200.load(build_if_missing=True)
+    B.set_arith(args.arith)
+    stream = torch.cuda.current_stream()
+    B.set_stream(stream.cuda_stream)
+
+    case, nlev, desc = workload(B, args.workload)
+    if args.levels:
+        nlev = args.levels
+    nin, nout = case.n_src, case.n_out
+    case.defset()
+
+    # synthetic analytic fields, generated once on the host and made resident in HBM before the timed region.
+    # every rank owns its own nlev levels (level k of rank r is analytic level r*nlev + k).
+    comps = 2 if case.vector else 1
+    h_in = [torch.empty((nlev, nin), dtype=torch.float32, pin_memory=True) for _ in range(comps)]
+    base = [case.source_uv(0) if case.vector else (case.source(0),)][0]
+    for c in range(comps):
+        b = torch.from_numpy(np.ascontiguousarray(base[c]).ravel())
+        for k in range(nlev):
+            h_in[c][k].copy_(b)
+            h_in[c][k].add_(0.01 * (rank * nlev + k))   # cheap per-level variation; interpolation is linear in the field
+    d_in = [h.cuda(non_blocking=True) for h in h_in]
+    d_out = [torch.empty((nlev, nout), dtype=torch.float32, device="cuda") for _ in range(comps)]
+    h_out = [torch.empty((nlev, nout), dtype=torch.float32, pin_memory=True) for _ in range(comps)]
+    torch.cuda.synchronize()
+
+    def step_dev():
+        if case.vector:
+            return B.ezuvint_batch(d_out[0], d_out[1], d_in[0], d_in[1], nlev)
+        return B.ezsint_batch(d_out[0], d_in[0], nlev)
+
+    def step_host():
+        if case.vector:
+            return B.ezuvint_batch(h_out[0], h_out[1], h_in[0], h_in[1], nlev)
+        return B.ezsint_batch(h_out[0], h_in[0], nlev)
+
+    rc = step_dev()   # builds the gridset (one-time K12-K15 cost, reported separately)
+    if rc < 0:
+        raise SystemExit("hot path failed rc=%d" % rc)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    B.lib.c_gdrls  # noqa (keep symbol referenced)
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---- device-resident timing: EXACTLY K steps, CUDA events on the launching stream ----
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    B.launch_count(reset=True)
+    barrier()
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_all0.record(stream)
+    for a, b in evs:
+        a.record(stream)
+        step_dev()
+        b.record(stream)
+    e_all1.record(stream)
+    barrier()
+    launches = B.launch_count()
+    total_ms = e_all0.elapsed_time(e_all1)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * nout * nlev / (ms_per_step * 1e-3)
+
+    # ---- end-to-end: host (pinned) buffers through the same C-ABI call, copies inside the timed region ----
+    for _ in range(2):
+        step_host()
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        step_host()
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    te = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item()) / e2e_steps
+    e2e_value = world * nout * nlev / (e2e_ms * 1e-3)
+
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_kind = measured_peak()
+    abytes = algorithmic_bytes(case, nlev)
+    kern_ms = statistics.mean(step_ms)   # one step == one launch of the dominant kernel (+ its launch gap)
+    achieved = abytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_kind": peak_kind, "kernel": "k_interp_fast<%s>" % {"nearest": 0, "linear": 1, "cubic": 3}[case.opts.get("interp_degree", "cubic")],
+                "algorithmic_bytes_per_launch": abytes, "kernel_ms": kern_ms}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and os.path.exists(REF_SO):
+        try:
+            v, ms, _, _ = cpu_reference_run(args.workload, min(args.cpu_sample_levels, nlev), cores, 2, 1)
+            cpu_baseline = {"value": v, "unit": unit, "cores": cores, "kind": "reference",
+                            "sample": "%d levels of the same workload, %d host threads (one c_ezdefset+c_ezsint stream per thread), %.0f ms/step" % (
+                                min(args.cpu_sample_levels, nlev), cores, ms)}
+        except Exception as ex:   # the baseline is reported, never required for the GPU number
+            cpu_baseline = {"value": None, "unit": unit, "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-on-f32",
+            "data": "synthetic",
+            "config": {"workload": desc, "levels_per_gpu": nlev, "n_src": nin, "n_out": nout, "arith": args.arith,
+                       "l2": "inputs larger than L2 (%.0f MB in + %.0f MB out per step)" % (comps * nlev * nin * 4 / 1e6, comps * nlev * nout * 4 / 1e6),
+                       "parallelism": "levels partitioned over %d GPU(s), replicated gridset" % world},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": comps * nlev * nin * 4, "d2h_bytes_per_step": comps * nlev * nout * 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -119,11 +119,11 @@ YANG_ROT = (0.0, 0.0, 90.0, 0.0)
 
 
 def yy_axes(res):
-    """Panel axes: ax 45-3*res ... 315+3*res, ay -45-3*res ... 45+3*res (res=0.15 gives 1841 x 641)."""
-    ni = int(round((270.0 + 6 * res) / res)) + 1
-    nj = int(round((90.0 + 6 * res) / res)) + 1
-    ax = (45.0 - 3 * res) + res * np.arange(ni)
-    ay = (-45.0 - 3 * res) + res * np.arange(nj)
+    """Panel axes: ax 42 ... 318, ay -48 ... 48 (a 3-degree halo around the 45..315 x -45..45 core; res=0.15 gives 1841 x 641)."""
+    ni = int(round(276.0 / res)) + 1
+    nj = int(round(96.0 / res)) + 1
+    ax = 42.0 + res * np.arange(ni)
+    ay = -48.0 + res * np.arange(nj)
     return ax.astype(np.float32), ay.astype(np.float32)
 
 

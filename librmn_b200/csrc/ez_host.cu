@@ -945,7 +945,7 @@ int32_t c_ezb200_set_stream(void *stream) {
     return 0;
 }
 int32_t c_ezb200_set_arith(int32_t mode) {
-    if (mode != 0 && mode != 1) return -1;
+    if (mode < 0 || mode > 2) return -1;
     S.arith = mode;
     return 0;
 }

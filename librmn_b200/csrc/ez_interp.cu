@@ -430,21 +430,26 @@ __device__ __noinline__ float zone_point(const FieldFetch &ff, const GridDev &g,
 // ---------------------------------------------------------------------------------------------------
 // the interpolation kernel: generic, reference-order arithmetic
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_interp_ref(InterpArgs a) {
-    int n = blockIdx.x * TPB + threadIdx.x;
-    if (n >= a.npts) return;
-    const float px = a.x[n], py = a.y[n];
-    const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
-    const bool yang = a.yy && (bits & ZB_YANG);
-    const GridDev &g = yang ? a.src2 : a.src;
-    const float *zbase = a.zin + (yang ? a.panel_stride : 0);
-    const uint8_t zbits = a.use_zones ? (uint8_t)(bits & 0x1f) : (uint8_t)0;
+__device__ __forceinline__ void ref_point_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ zbase, int n, float px, float py,
+                                               uint8_t zbits) {
     for (int f = 0; f < a.nfields; f++) {
         FieldFetch ff = make_fetch(g, zbase + (long)f * a.in_stride, a.o.sym_sign);
         float v = interp_point(ff, g, a.o.degree, px, py);
         if (zbits) v = zone_point(ff, g, a.o, zbits, a.fs, f, px, py, v);
         a.zout[(long)f * a.out_stride + n] = v;
     }
+}
+
+__global__ void __launch_bounds__(TPB) k_interp_ref(const __grid_constant__ InterpArgs a) {
+    int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= a.npts) return;
+    const float px = a.x[n], py = a.y[n];
+    const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
+    const uint8_t zbits = a.use_zones ? (uint8_t)(bits & 0x1f) : (uint8_t)0;
+    if (a.yy && (bits & ZB_YANG))
+        ref_point_body(a.src2, a, a.zin + a.panel_stride, n, px, py, zbits);
+    else
+        ref_point_body(a.src, a, a.zin, n, px, py, zbits);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -587,7 +592,7 @@ void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldSc
 
 int interp(const InterpArgs &a, cudaStream_t s) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
-    if (a.o.arith == 1 && launch_fast(a, s)) return 1;
+    if (a.o.arith >= 1 && launch_fast(a, s)) return 1;
     int nb = (a.npts + TPB - 1) / TPB;
     k_interp_ref<<<nb, TPB, 0, s>>>(a);
     return 1;

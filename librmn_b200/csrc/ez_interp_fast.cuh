@@ -1,11 +1,294 @@
-// librmn_b200/csrc/ez_interp_fast.cuh -- weight-form ("arith = 1") specialisations of the interpolation kernel.
-// Included by ez_interp.cu inside its translation unit.
+// librmn_b200/csrc/ez_interp_fast.cuh -- the production interpolation kernel ("arith = 1").
+// Included by ez_interp.cu inside its translation unit (uses its evaluators for the rare zone points).
+//
+// One thread per target point.  A per-point PLAN (element offsets of the stencil and the interpolation
+// weights) is computed once from (x, y); the level loop then only gathers, multiplies and stores:
+//   nearest : 1 load                                -- bit-identical to ez_rgdint_0
+//   linear  : 4 loads + 3 zlin in fp64              -- the reference's own operation order (ez_rgdint_1_*,
+//                                                     ez_irgdint_1_*), only hoisted out of the level loop
+//   cubic   : 16 loads + 20 fp64 FMAs               -- weight form: zo = sum_b wy_b * (sum_a wx_a * z_ab);
+//             wx, wy are the cubic8.cdk polynomial (regular grids) or the Newton basis built from the same
+//             cx/cy tables (irregular grids), evaluated in fp64.  Rounding differs from the reference's
+//             Horner/Newton order at the 1e-16 (fp64) level -- or 1e-7 of the field magnitude for
+//             ez_irgdint_3_nw, whose reference form rounds partial results to fp32 -- far inside the
+//             1e-5-of-range tolerance.
+// Why fp64 and not fp32: 20 DFMA/point-level keep the FP64 pipe under the L1 gather bound (64 B/point at
+// 128 B/clk/SM), so fp32 would buy nothing while costing accuracy on large-offset fields.
 #pragma once
 
 namespace {
-// returns false when no specialisation covers this launch (the caller falls back to k_interp_ref)
-bool launch_fast(const InterpArgs &a, cudaStream_t s) {
-    (void)a; (void)s;
-    return false;
+
+struct PlanLin {
+    int o00, o10, o01, o11;   // element offsets of (i,j) (ip1,j) (i,j+1) (ip1,j+1)
+    double dx, dy;
+};
+struct PlanCub {
+    int c[4];                 // element offsets of the four columns within a row (0-based)
+    int r0;                   // element offset of row j-1
+    int ni;                   // row pitch
+    double wx[4], wy[4];
+};
+
+__device__ __forceinline__ bool is_irregular(const GridDev &g) { return g.grtyp == '#' || g.grtyp == 'Z' || g.grtyp == 'G'; }
+
+// nearest: ez_rgdint_0.inc:27-32
+__device__ __forceinline__ int plan_nearest(const GridDev &g, float px, float py) {
+    int i = min(g.ni, max(1, f_nint(px)));
+    int j = min(g.j2, max(g.j1, f_nint(py)));
+    return (j - g.j1) * g.ni + (i - 1);
 }
+
+// linear: index and dx/dy logic of ez_rgdint_1_nw/_w and ez_irgdint_1_nw/_w
+__device__ __forceinline__ PlanLin plan_linear(const GridDev &g, float px, float py) {
+    PlanLin p;
+    const int ni = g.ni, j1 = g.j1, j2 = g.j2;
+    int i, ip1, j;
+    if (is_irregular(g)) {
+        if (g.ext == 0) {
+            i = min(ni - 1, max(1, f_ifix(px)));
+            j = min(g.nj - 1, max(1, f_ifix(py)));
+            ip1 = i + 1;
+            float axi = __ldg(g.ax + i - 1), axi1 = __ldg(g.ax + i), ayj = __ldg(g.ay + j - 1), ayj1 = __ldg(g.ay + j);
+            double x1 = axi, x2 = axi1;
+            double x = (double)axi + (x2 - x1) * (double)(px - (float)i);
+            double y = (double)(ayj + (ayj1 - ayj) * (py - (float)j));
+            p.dx = (x - x1) / (x2 - x1);
+            p.dy = (y - (double)ayj) / (double)(ayj1 - ayj);
+        } else {
+            const int wrap = g.ext, limite = ni + 2 - wrap;
+            i = min(ni - 2 + wrap, max(1, f_ifix(px)));
+            j = min(j2 - 1, max(j1 + 1, f_ifix(py)));
+            if (j < 0) j = j - 1;
+            ip1 = i + 1;
+            double x1 = __ldg(g.ax + i - 1), x2 = 0.0;
+            if (ip1 <= ni) x2 = __ldg(g.ax + ip1 - 1);
+            if (i == (ni - 2 + wrap)) {
+                ip1 = (limite + i + 1) % limite;
+                x2 = (double)(__ldg(g.ax + 1) + __ldg(g.ax + ni - 1));
+            }
+            float ayj = __ldg(g.ay + (j - j1)), ayj1 = __ldg(g.ay + (j + 1 - j1));
+            double x = x1 + (x2 - x1) * (double)(px - (float)i);
+            double y = (double)(ayj + (ayj1 - ayj) * (py - (float)j));
+            p.dx = (x - x1) / (x2 - x1);
+            p.dy = (y - (double)ayj) / (double)(ayj1 - ayj);
+        }
+    } else {
+        if (g.ext == 2) {
+            const int wrap = 2, limite = ni + 2 - wrap;
+            i = min(ni - 2 + wrap, max(1, f_ifix(px)));
+            ip1 = i + 1;
+            if (i == (ni - 2 + wrap)) ip1 = (limite + i + 1) % limite;
+        } else {
+            i = min(ni - 1, max(1, f_ifix(px)));
+            ip1 = i + 1;
+        }
+        j = min(j2 - 1, max(j1, f_ifix(py)));
+        p.dx = (double)(px - (float)i);
+        p.dy = (double)(py - (float)j);
+    }
+    const int r = (j - j1) * ni;
+    p.o00 = r + i - 1;
+    p.o10 = r + ip1 - 1;
+    p.o01 = r + ni + i - 1;
+    p.o11 = r + ni + ip1 - 1;
+    return p;
+}
+
+// Newton-basis weights for nodes with reciprocal tables c[0..5] and offsets t1 = x-x1, t2 = x-x2, t3 = x-x3:
+//   b = z1 + t1 (a2 + t2 (a3 + a4 t3))   with a2..a4 as in ez_irgdint_3_nw.inc:85-87
+__device__ __forceinline__ void newton_weights(const double c[6], double t1, double t2, double t3, double w[4]) {
+    const double P1 = t1, P2 = t1 * t2, P3 = P2 * t3;
+    const double c21 = c[1] * c[0], s31 = c[2] + c[0];
+    const double k2 = c[1] * s31;                       // c2 (c3 + c1)
+    const double k3 = c[1] * c[2];                      // c2 c3
+    w[0] = 1.0 - P1 * c[0] + P2 * c21 - P3 * (c[3] * c21);
+    w[1] = P1 * c[0] - P2 * k2 + P3 * (c[3] * (c[4] * c[2] + k2));
+    w[2] = P2 * k3 - P3 * (c[3] * (c[4] * (c[5] + c[2]) + k3));
+    w[3] = P3 * (c[3] * c[4] * c[5]);
+}
+
+// cubic8.cdk:3 expanded in the samples (fp32-rounded literals kept)
+__device__ __forceinline__ void cubic_weights(double d, double w[4]) {
+    const double c6 = (double)0.1666666666666f, c3 = (double)0.3333333333333f, h = 0.5;
+    w[0] = ((-c6 * d + h) * d - c3) * d;
+    w[1] = ((h * d - 1.0) * d - h) * d + 1.0;
+    w[2] = ((-h * d + h) * d + 1.0) * d;
+    w[3] = (c6 * d * d - c6) * d;
+}
+
+__device__ __forceinline__ PlanCub plan_cubic(const GridDev &g, float px, float py) {
+    PlanCub p;
+    const int ni = g.ni, j1 = g.j1, j2 = g.j2;
+    p.ni = ni;
+    int i, im1, ip1, ip2;
+    const int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
+    if (is_irregular(g)) {
+        const int ny = j2 - j1 + 1;
+        const float *ay = g.ay - j1;
+        const float aym = __ldg(ay + j - 1), ay0 = __ldg(ay + j), ayp = __ldg(ay + j + 1);
+        const double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
+        double cx[6], cy[6];
+        float x1, x2, x3, x4;
+        int nxt;
+        if (g.ext == 0) {
+            i = min(g.i2 - 2, max(g.i1 + 1, f_ifix(px)));
+            im1 = i - 1; ip1 = i + 1; ip2 = i + 2;
+            x1 = __ldg(g.ax + im1 - 1); x2 = __ldg(g.ax + i - 1); x3 = __ldg(g.ax + ip1 - 1); x4 = __ldg(g.ax + ip2 - 1);
+            nxt = g.i2 - g.i1 + 1;
+        } else {
+            const int wrap = g.ext;
+            i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
+            seam_x(wrap, ni, g.ax, i, false, im1, ip1, ip2, x1, x2, x3, x4);
+            nxt = ni;
+        }
+        (void)x4;
+        const double x = (double)(x2 + (x3 - x2) * (px - (float)i));
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            cx[k] = (double)__ldg(g.cx + (long)k * nxt + (i - 1));
+            cy[k] = (double)__ldg(g.cy + (long)k * ny + (j - j1));
+        }
+        newton_weights(cx, x - (double)x1, x - (double)x2, x - (double)x3, p.wx);
+        newton_weights(cy, y - (double)aym, y - (double)ay0, y - (double)ayp, p.wy);
+    } else {
+        rgd3_cols(g.ext == 0 ? 0 : 1, ni, g.ext, px, i, im1, ip1, ip2);
+        cubic_weights((double)(px - (float)i), p.wx);
+        cubic_weights((double)(py - (float)j), p.wy);
+    }
+    p.c[0] = im1 - 1; p.c[1] = i - 1; p.c[2] = ip1 - 1; p.c[3] = ip2 - 1;
+    p.r0 = (j - 1 - j1) * ni;
+    return p;
+}
+
+__device__ __forceinline__ float eval_cubic(const PlanCub &p, const float *__restrict__ z) {
+    const float *r = z + p.r0;
+    double acc = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const float z0 = __ldg(r + p.c[0]), z1 = __ldg(r + p.c[1]), z2 = __ldg(r + p.c[2]), z3 = __ldg(r + p.c[3]);
+        double s = p.wx[0] * (double)z0;
+        s = fma(p.wx[1], (double)z1, s);
+        s = fma(p.wx[2], (double)z2, s);
+        s = fma(p.wx[3], (double)z3, s);
+        acc = fma(p.wy[b], s, acc);
+        r += p.ni;
+    }
+    return (float)acc;
+}
+
+// fp32 "difference form" of the same weight-form cubic (arith = 2): with zc = z(i,j) the stencil centre,
+//   zo = zc + [ sum_b wy_b sum_a wx_a (z_ab - zc) + zc * ((sum wx)(sum wy) - 1) ]
+// The differences are exact or nearly so (Sterbenz), so the fp32 rounding error scales with the LOCAL
+// variation of the field (<= its range), not with its magnitude: ~3e-7 of the range, with no fp32->fp64
+// conversions (16/clk/SM on this part) and no FP64 pipe use in the level loop.
+struct PlanCubF {
+    int c[4];
+    int r0, ni;
+    float wx[4], wy[4];
+    float sm1;                // (sum wx)(sum wy) - 1, evaluated in fp64
+};
+__device__ __forceinline__ PlanCubF to_f32(const PlanCub &p) {
+    PlanCubF q;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { q.c[k] = p.c[k]; q.wx[k] = (float)p.wx[k]; q.wy[k] = (float)p.wy[k]; }
+    q.r0 = p.r0; q.ni = p.ni;
+    q.sm1 = (float)((p.wx[0] + p.wx[1] + p.wx[2] + p.wx[3]) * (p.wy[0] + p.wy[1] + p.wy[2] + p.wy[3]) - 1.0);
+    return q;
+}
+__device__ __forceinline__ float eval_cubic_f32(const PlanCubF &p, const float *__restrict__ z) {
+    const float *r = z + p.r0;
+    float v[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) v[b][a] = __ldg(r + p.c[a]);
+        r += p.ni;
+    }
+    const float zc = v[1][1];
+    float acc = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        float s = p.wx[0] * (v[b][0] - zc);
+        s = fmaf(p.wx[1], v[b][1] - zc, s);
+        s = fmaf(p.wx[2], v[b][2] - zc, s);
+        s = fmaf(p.wx[3], v[b][3] - zc, s);
+        acc = fmaf(p.wy[b], s, acc);
+    }
+    return zc + fmaf(zc, p.sm1, acc);
+}
+
+__device__ __forceinline__ float eval_linear(const PlanLin &p, const float *__restrict__ z) {
+    const double z00 = (double)__ldg(z + p.o00), z10 = (double)__ldg(z + p.o10);
+    const double z01 = (double)__ldg(z + p.o01), z11 = (double)__ldg(z + p.o11);
+    const double y2 = zlin(z00, z10, p.dx);
+    const double y3 = zlin(z01, z11, p.dx);
+    return (float)zlin(y2, y3, p.dy);
+}
+
+// DEG = 0 nearest, 1 linear, 3 cubic (fp64 weight form), 4 cubic (fp32 difference form).  Requires plain field access (no hemispheric mirror, no y inversion).
+// The grid descriptor is taken by reference straight from kernel-parameter (constant-bank) space: the Yin/Yang
+// choice is a branch around two instantiations rather than a pointer select, which would force a local copy.
+template <int DEG>
+__device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ z, int n, float px, float py,
+                                           uint8_t zbits) {
+    float *zo = a.zout + n;
+    const int nf = a.nfields;
+    const long is = a.in_stride, os = a.out_stride;
+    if (zbits == 0) {
+        if (DEG == 0) {
+            const int o = plan_nearest(g, px, py);
+#pragma unroll 4
+            for (int f = 0; f < nf; f++) zo[f * os] = __ldg(z + f * is + o);
+        } else if (DEG == 1) {
+            const PlanLin p = plan_linear(g, px, py);
+#pragma unroll 2
+            for (int f = 0; f < nf; f++) zo[f * os] = eval_linear(p, z + f * is);
+        } else if (DEG == 3) {
+            const PlanCub p = plan_cubic(g, px, py);
+#pragma unroll 2
+            for (int f = 0; f < nf; f++) zo[f * os] = eval_cubic(p, z + f * is);
+        } else {
+            const PlanCubF p = to_f32(plan_cubic(g, px, py));
+#pragma unroll 2
+            for (int f = 0; f < nf; f++) zo[f * os] = eval_cubic_f32(p, z + f * is);
+        }
+        return;
+    }
+    // rare: a point in a polar / outside zone -- reference-order evaluators (ez_corrval semantics)
+    for (int f = 0; f < nf; f++) {
+        FieldFetch ff = make_fetch(g, z + f * is, a.o.sym_sign);
+        float v = 0.f;
+        if (!(zbits & (ZB_POLE_NORD | ZB_POLE_SUD)) || a.o.vector) v = interp_point(ff, g, a.o.degree, px, py);
+        zo[f * os] = zone_point(ff, g, a.o, zbits, a.fs, f, px, py, v);
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ InterpArgs a) {
+    const int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= a.npts) return;
+    const float px = a.x[n], py = a.y[n];
+    const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
+    const uint8_t zbits = a.use_zones ? (uint8_t)(bits & 0x1f) : (uint8_t)0;
+    if (a.yy && (bits & ZB_YANG))
+        point_body<DEG>(a.src2, a, a.zin + a.panel_stride, n, px, py, zbits);
+    else
+        point_body<DEG>(a.src, a, a.zin, n, px, py, zbits);
+}
+
+bool launch_fast(const InterpArgs &a, cudaStream_t s) {
+    if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
+    if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
+    const int nb = (a.npts + TPB - 1) / TPB;
+    switch (a.o.degree) {
+        case EZ_NEAREST: k_interp_fast<0><<<nb, TPB, 0, s>>>(a); return true;
+        case EZ_LINEAR: k_interp_fast<1><<<nb, TPB, 0, s>>>(a); return true;
+        case EZ_CUBIC:
+            if (a.o.arith == 2) k_interp_fast<4><<<nb, TPB, 0, s>>>(a);
+            else k_interp_fast<3><<<nb, TPB, 0, s>>>(a);
+            return true;
+        default: return false;
+    }
+}
+
 }  // namespace

@@ -1,0 +1,365 @@
+"""GPU parity tests: the CUDA path (libezb200.so, through its C ABI) against the oracle on the same inputs.
+
+Bar (BASELINE.json north_star): bit-exact stencil indices / zone classes / masks / nearest-neighbour picks
+except at exact coordinate ties, interpolated fp32 values within 1e-5 of the source field's range.
+
+Coordinates that go through fp32 libm calls in the reference (sinf, asinf, atan2f ... in ez_lac / ez_cal /
+llfxy) can differ from a glibc-hosted run by one ulp, because glibc's fp32 functions are not correctly
+rounded and the device evaluates them through fp64 (DESIGN.md "coordinate parity").  A point whose oracle
+coordinate sits within a few ulp of a decision boundary (x.5 for nearest picks, an integer for zone
+tests) is a "near tie": such points are counted, bounded, and excluded from the bit-exact comparison.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from librmn_b200 import configs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ezref_small.npz")
+TOL = 1e-5          # of the source field's range (north_star)
+ULPS = 8            # coordinate agreement, in fp32 ulps of the coordinate
+
+
+def ulp_diff(a, b):
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    return np.abs(a.astype(np.float64) - b) / np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32))
+
+
+def oracle_xy(ref, case):
+    shape = case.dst_shape
+    lat = np.zeros(shape, np.float32)
+    lon = np.zeros(shape, np.float32)
+    assert ref.gdll(case.gdout, lat, lon) == 0
+    x = np.zeros(shape, np.float32)
+    y = np.zeros(shape, np.float32)
+    assert ref.gdxyfll(case.gdin, x, y, lat, lon.copy()) == 0
+    return x.ravel(), y.ravel()
+
+
+def coord_eps(case, xr, yr):
+    """Absolute agreement expected between two evaluations of the source-index coordinates (index units).
+
+    Two contributions: ULPS ulp of the coordinate itself, and -- for sources reached through a rotated or
+    lat-lon frame -- a few ulp of the fp32 angle (up to 360 deg, ulp 3.05e-5) divided by the source cell size,
+    which is the reference's own rounding noise in `(px - ax(i)) / (ax(i+1) - ax(i))` (ez_ll2igd.inc:82-83)."""
+    lon, lat = np.asarray(case.src_lon, np.float64), np.asarray(case.src_lat, np.float64)
+    cell = min(np.abs(np.diff(lon, axis=1)).min(), np.abs(np.diff(lat, axis=0)).min())
+    ang = 4 * 3.05e-5 / cell
+    ex = ULPS * np.spacing(np.maximum(np.abs(xr), 1).astype(np.float32)).astype(np.float64) + ang
+    ey = ULPS * np.spacing(np.maximum(np.abs(yr), 1).astype(np.float32)).astype(np.float64) + ang
+    return ex, ey
+
+
+def near_half(v, eps):
+    f = v - np.floor(v)
+    return np.abs(f - 0.5) < eps
+
+
+def near_int(v, eps):
+    return np.abs(v - np.round(v)) < eps
+
+
+def plain_cases(lib, degree):
+    return [c for c in cases.small_cases(lib, degree) if not c.name.startswith("C2")]
+
+
+# ---------------------------------------------------------------------------------------------------
+# gridset: x, y, zone bits
+# ---------------------------------------------------------------------------------------------------
+def zone_bits_from_xy(ref, case, x, y):
+    """ez_defzones.c:44-109 + ez_defzone_*.c restated on the ORACLE's coordinates (numpy)."""
+    rc, ni, nj, grtyp, ig, grref, igref = ref.ezgxprm(case.gdin)
+    ax0 = ax1 = None
+    extrap = False
+    if grtyp in "NS":
+        extrap = True
+    # j1/j2 and the wrap extension are not exposed by the public API; the small cases only use sources whose
+    # logical row range is 1..nj, and decide EZ_EXTRAP from the geometry exactly as ez_defzones does
+    if grtyp == "L":
+        lat0, lon0, dlat, dlon = ref.cigaxg("L", *ig)
+        glob = (lat0 - dlat <= -90.0 + 0.01 * dlat) and (lat0 + (nj - 1) * dlat + dlat >= 90.0 - 0.01 * dlat) and (dlon * ni > 360.0 - 0.01 * dlon)
+        extrap = not glob
+    if grtyp == "Z":
+        ax0, ax1 = case.src_lon[0, 0], case.src_lon[0, -1]
+        extrap = 358.0 > (np.float32(ax1) - np.float32(ax0))
+    bits = np.zeros(x.shape, np.uint8)
+    if extrap:
+        ix = np.trunc(x.astype(np.float64) + 0.5).astype(np.int64)
+        iy = np.trunc(y.astype(np.float64) + 0.5).astype(np.int64)
+        bits[(ix < 1) | (iy < 1) | (ix > ni) | (iy > nj)] |= 1
+        return bits, extrap
+    if grtyp == "Z" and grref == "E":
+        ypn, yps = np.float32(nj + 0.5), np.float32(0.5)
+    else:
+        xx = np.zeros(2, np.float32)
+        yy = np.zeros(2, np.float32)
+        ref.gdxyfll(case.gdin, xx, yy, np.array([90.0, -90.0], np.float32), np.array([0.0, 0.0], np.float32))
+        ypn, yps = yy[0], yy[1]
+    bits[np.abs((y - ypn).astype(np.float64)) < 1e-3] |= 8
+    bits[np.abs((y - yps).astype(np.float64)) < 1e-3] |= 16
+    bits[np.trunc(y).astype(np.int64) < 2] |= 4
+    bits[np.trunc(y).astype(np.int64) > nj - 2] |= 2
+    return bits, extrap
+
+
+def test_gridset_coordinates_and_zone_bits(ezb, ezref, cuda_ok):
+    total = ties = 0
+    for c_b, c_r in zip(plain_cases(ezb, "linear"), plain_cases(ezref, "linear")):
+        if "_scalar_extrap_" in c_b.name:
+            continue
+        c_b.defset()
+        c_r.defset()
+        xb, yb, zb, counts = ezb.get_gridset(c_b.gdout, c_b.gdin, c_b.n_out)
+        xr, yr = oracle_xy(ezref, c_r)
+        # (1) coordinates agree to rounding noise (see coord_eps)
+        ex, ey = coord_eps(c_b, xr, yr)
+        ux = np.abs(xb.astype(np.float64) - xr) / ex
+        uy = np.abs(yb.astype(np.float64) - yr) / ey
+        far = (np.abs(xr) > 4 * c_b.src_shape[1]) | (np.abs(yr) > 4 * c_b.src_shape[0])   # ill-conditioned, far outside the source
+        assert np.nanmax(ux[~far]) <= 1 and np.nanmax(uy[~far]) <= 1, (c_b.name, np.nanmax(ux[~far]), np.nanmax(uy[~far]))
+        exact = float(np.mean((xb == xr) & (yb == yr)))
+        # (2) zone bits are bit-exact wherever the oracle's coordinate is not within rounding noise of a decision boundary
+        bits_r, extrap = zone_bits_from_xy(ezref, c_r, xr, yr)
+        tie = (near_half(xr, ex) | near_half(yr, ey)) if extrap else near_int(yr, ey)
+        bad = ((zb & 0x1f) != bits_r) & ~tie
+        assert not bad.any(), "%s: %d zone-bit mismatches away from ties" % (c_b.name, int(bad.sum()))
+        assert counts[0] == int(((zb & 1) != 0).sum())
+        total += xb.size
+        ties += int(tie.sum())
+        print("%-28s exact-xy %.4f  zone counts %s" % (c_b.name, exact, counts[:5]))
+    # the reduced grids are commensurate on purpose (both poles, seam, borders): whole rows sit on decision boundaries
+    assert ties < 0.10 * total
+
+
+# ---------------------------------------------------------------------------------------------------
+# values
+# ---------------------------------------------------------------------------------------------------
+def compare(name, out_b, out_r, rng, tie_mask=None, tol=TOL):
+    """Every point within tol of range, except near-tie points (returned as a count and bounded by the caller)."""
+    d = np.abs(out_b.astype(np.float64) - out_r.astype(np.float64)) / rng
+    bad = d > tol
+    flipped = 0
+    if tie_mask is not None:
+        flipped = int((bad & tie_mask).sum())
+        bad &= ~tie_mask
+    assert not bad.any(), "%s: %d points off by more than %g of range (max %g)" % (name, int(bad.sum()), tol, d[bad].max())
+    return float(d[~tie_mask].max() if tie_mask is not None else d.max()), int((out_b.view(np.uint32) != out_r.view(np.uint32)).sum()), flipped
+
+
+@pytest.mark.parametrize("arith", [0, 1, 2])
+@pytest.mark.parametrize("degree", cases.DEGREES)
+def test_values_against_oracle(ezb, ezref, cuda_ok, degree, arith):
+    ezb.set_arith(arith)
+    try:
+        for c_b, c_r in zip(cases.small_cases(ezb, degree), cases.small_cases(ezref, degree)):
+            rc_b, out_b = cases.run_case(ezb, c_b)
+            rc_r, out_r = cases.run_case(ezref, c_r)
+            assert rc_b == rc_r, c_b.name
+            rng = cases.field_range(c_b)
+            tie = None
+            if c_b.name.startswith("C2"):
+                # 'U' source: per-panel coordinates come from the product's own gridset (the reference's c_gdxyfll
+                # on a 'U' grid answers a different question, gdxyfll.c:199-236)
+                xr, yr, _, _ = ezb.get_gridset(c_b.gdout, c_b.gdin, c_b.n_out)
+                ex, ey = coord_eps(c_b, xr, yr)
+                tie = np.broadcast_to((near_half(xr, ex) | near_half(yr, ey)).reshape(c_b.dst_shape), out_b.shape) if degree == "nearest" else None
+            else:
+                xr, yr = oracle_xy(ezref, c_r)
+                ex, ey = coord_eps(c_b, xr, yr)
+                tie = np.zeros(xr.shape, bool)
+                if degree == "nearest" or c_b.opts.get("extrap_degree") == "nearest":
+                    tie |= near_half(xr, ex) | near_half(yr, ey)      # exact coordinate ties of a nearest pick
+                # a point flips zone class when (int)(x+0.5) crosses the border (DEHORS) or (int)y crosses a polar-cap row
+                tie |= (near_half(xr, ex) | near_half(yr, ey)) & ((xr < 1.5) | (yr < 1.5) | (xr > c_b.src_shape[1] - 0.5) | (yr > c_b.src_shape[0] - 0.5))
+                tie |= near_int(yr, ey) & ((yr < 2.5) | (yr > c_b.src_shape[0] - 2.5))
+                tie = np.broadcast_to(tie.reshape(c_b.dst_shape), out_b.shape)
+            mx, nbit, flipped = compare("%s arith=%d" % (c_b.name, arith), out_b, out_r, rng, tie)
+            assert flipped <= max(4, 0.02 * out_b.size), "%s: too many flipped near ties (%d)" % (c_b.name, flipped)
+            print("%-44s a%d rc=%d max|d|/range=%.2e bit-diff=%d/%d flipped-ties=%d" % (c_b.name, arith, rc_b, mx, nbit, out_b.size, flipped))
+    finally:
+        ezb.set_arith(1)
+
+
+@pytest.mark.parametrize("degree", cases.DEGREES)
+def test_values_against_golden_vectors(ezb, cuda_ok, degree):
+    """Same comparison against the committed oracle outputs (works on a box without the oracle library); near ties
+    are located with the product's own device-resident coordinates."""
+    g = np.load(GOLDEN)
+    for c in cases.small_cases(ezb, degree):
+        rc, out = cases.run_case(ezb, c)
+        assert rc == int(g[c.name + "__rc"]), c.name
+        ref = g[c.name + "__out"]
+        rng = cases.field_range(c)
+        x, y, zb, _ = ezb.get_gridset(c.gdout, c.gdin, c.n_out)
+        ex, ey = coord_eps(c, x, y)
+        tie = np.zeros(x.shape, bool)
+        if degree == "nearest" or c.opts.get("extrap_degree") == "nearest":
+            tie |= near_half(x, ex) | near_half(y, ey)
+        tie |= (near_half(x, ex) | near_half(y, ey)) & ((x < 1.5) | (y < 1.5) | (x > c.src_shape[1] - 0.5) | (y > c.src_shape[0] - 0.5))
+        tie |= near_int(y, ey) & ((y < 2.5) | (y > c.src_shape[0] - 2.5))
+        tie = np.broadcast_to(tie.reshape(c.dst_shape), out.shape)
+        mx, nbit, flipped = compare(c.name + " vs golden", out, ref, rng, tie)
+        assert flipped <= max(4, 0.02 * out.size), c.name
+
+
+def test_nearest_picks_are_source_samples(ezb, cuda_ok):
+    """Nearest-neighbour output is a gather: every value must be bit-identical to some source sample, and equal
+    to the sample at (nint(x), nint(y)) of the device-resident gridset."""
+    for c in plain_cases(ezb, "nearest"):
+        if c.vector or "_scalar_extrap_" in c.name:
+            continue
+        rs = np.random.default_rng(11)
+        c.defset()
+        ezb.ezsetopt("polar_correction", "no")
+        zin = rs.standard_normal(c.src_shape).astype(np.float32)
+        zout = np.zeros(c.dst_shape, np.float32)
+        assert ezb.ezsint(zout, zin) >= 0
+        x, y, zb, _ = ezb.get_gridset(c.gdout, c.gdin, c.n_out)
+        nj, ni = c.src_shape
+        ii = np.clip(np.where(x >= 0, np.floor(x + 0.5), np.ceil(x - 0.5)).astype(np.int64), 1, ni) - 1
+        jj = np.clip(np.where(y >= 0, np.floor(y + 0.5), np.ceil(y - 0.5)).astype(np.int64), 1, nj) - 1
+        assert np.array_equal(zout.ravel(), zin[jj, ii]), c.name
+        ezb.ezsetopt("polar_correction", "yes")
+
+
+def test_yinyang_panel_selection_matches_oracle(ezb, ezref, cuda_ok):
+    outs = []
+    for lib in (ezb, ezref):
+        c = configs.c2(lib, res_src=3.0, res_dst=2.5, degree="nearest")
+        c.defset()
+        nj2 = c.src_shape[0]
+        zin = np.ones(c.src_shape, np.float32)
+        zin[nj2 // 2:] = 2.0
+        z = np.zeros(c.dst_shape, np.float32)
+        assert lib.ezsint(z, zin) == 0
+        outs.append(z)
+    diff = int((outs[0] != outs[1]).sum())
+    assert diff <= 2, "panel choice differs at %d points" % diff   # only exact ties on the mask border may flip
+
+
+def test_mask_transfer_matches_oracle(ezb, ezref, cuda_ok):
+    for alg in ("distance", "linear"):
+        res = []
+        for lib in (ezb, ezref):
+            c = configs.c3(lib, scale=32, degree="linear")
+            c.vector = False
+            c.defset()
+            lib.ezsetopt("cloud_interp_alg", alg)
+            z = np.zeros(c.dst_shape, np.float32)
+            lib.ezsint(z, c.source())          # the reference needs the gridset coordinates computed first
+            rs = np.random.default_rng(5)
+            mask_in = (rs.uniform(size=c.src_shape) > 0.2).astype(np.int32)
+            mask_out = np.full(c.dst_shape, -1, np.int32)
+            assert lib.ezsint_mask(mask_out, mask_in) == 0
+            res.append(mask_out)
+            lib.ezsetopt("cloud_interp_alg", "distance")
+        xr, yr = oracle_xy(ezref, c)
+        ex, ey = coord_eps(c, xr, yr)
+        tie = (near_half(xr, ex) | near_half(yr, ey) | near_int(xr, ex) | near_int(yr, ey)).reshape(c.dst_shape)
+        bad = (res[0] != res[1]) & ~tie
+        assert not bad.any(), "%s: %d mask mismatches" % (alg, int(bad.sum()))
+        assert set(np.unique(res[0])) <= {0, 1}
+
+
+# ---------------------------------------------------------------------------------------------------
+# API-level consistency of the CUDA path with itself
+# ---------------------------------------------------------------------------------------------------
+def test_batch_call_equals_single_calls(ezb, cuda_ok):
+    for c in (configs.c5(ezb, 3.0, 2.5, "cubic"), configs.c2(ezb, 3.0, 2.5, "cubic"), configs.c1(ezb, 96, "linear")):
+        c.defset()
+        nf = 5
+        zin = np.stack([c.source(k) for k in range(nf)])
+        single = np.zeros((nf,) + c.dst_shape, np.float32)
+        for k in range(nf):
+            assert ezb.ezsint(single[k], zin[k]) >= 0
+        batch = np.zeros_like(single)
+        assert ezb.ezsint_batch(batch, zin, nf) >= 0
+        assert np.array_equal(single, batch), c.name
+
+
+def test_device_pointers_equal_host_pointers(ezb, cuda_ok):
+    import torch
+    c = configs.c3(ezb, scale=16, degree="cubic")
+    c.defset()
+    u, v = c.source_uv()
+    uo = np.zeros(c.dst_shape, np.float32)
+    vo = np.zeros(c.dst_shape, np.float32)
+    rc_h = ezb.ezuvint(uo, vo, u, v)
+    du, dv = torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda()
+    duo, dvo = torch.empty(c.dst_shape, device="cuda"), torch.empty(c.dst_shape, device="cuda")
+    rc_d = ezb.ezuvint(duo, dvo, du, dv)
+    torch.cuda.synchronize()
+    assert rc_h == rc_d == 2
+    assert np.array_equal(duo.cpu().numpy(), uo) and np.array_equal(dvo.cpu().numpy(), vo)
+    before = ezb.launch_count(reset=True)
+    ezb.ezuvint(duo, dvo, du, dv)
+    assert ezb.launch_count() >= 3 and before >= 0      # u gather, v gather, rotation: CUDA kernels, not a fallback
+
+
+def test_same_grid_is_a_copy_and_undefined_set_fails(ezb, cuda_ok):
+    g = configs.def_L(ezb, 40, 20, -10.0, 10.0, 1.0, 1.0)
+    ezb.ezdefset(g, g)
+    z = np.random.default_rng(1).standard_normal((20, 40)).astype(np.float32)
+    out = np.zeros_like(z)
+    assert ezb.ezsint(out, z) == 1 and np.array_equal(out, z)
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arith", [0, 1, 2])
+@pytest.mark.parametrize("degree", cases.DEGREES)
+def test_coincident_nodes_reproduce_samples_exactly(ezb, cuda_ok, degree, arith):
+    """Global 0.25 deg 'L' source (1440 x 721, wrap extension 2) -> 0.5 deg 'L' target between 80S and 80N whose nodes
+    coincide with source nodes (all coordinates are exact dyadic numbers): dx = dy = 0 everywhere, so every degree
+    and every arithmetic mode must return the source samples BIT-exactly -- indices, wrap-around columns at the
+    seam and weights checked on 230 400 points."""
+    import torch
+    gdin = configs.def_L(ezb, 1440, 721, -90.0, 0.0, 0.25, 0.25)
+    gdout = configs.def_L(ezb, 720, 321, -80.0, 0.0, 0.5, 0.5)
+    c = configs.Case("coincident", ezb)
+    c.opts = {"interp_degree": degree}
+    c.apply_options()
+    ezb.set_arith(arith)
+    try:
+        assert ezb.ezdefset(gdout, gdin) == 1
+        zin = torch.randn((721, 1440), device="cuda", dtype=torch.float32)
+        zout = torch.empty((321, 720), device="cuda", dtype=torch.float32)
+        assert ezb.ezsint(zout, zin) == 0
+        torch.cuda.synchronize()
+    finally:
+        ezb.set_arith(1)
+    x, y, zb, counts = ezb.get_gridset(gdout, gdin, zout.numel())
+    assert np.array_equal(x, np.round(x)) and np.array_equal(y, np.round(y)) and not counts[:5].any()
+    assert torch.equal(zout, zin[40:681:2, 0:1440:2])
+
+
+def test_full_size_linearity_and_constants(ezb, cuda_ok):
+    """C2 at full size (U 2 x 1841 x 641 -> L 3600 x 1801, cubic): interp(a f + b g) = a interp(f) + b interp(g),
+    constants are preserved, and a batch of levels equals level-by-level calls."""
+    import torch
+    c = configs.c2(ezb, 0.15, 0.1, "cubic")
+    c.defset()
+    f = torch.from_numpy(c.source(0)).cuda()
+    g = torch.from_numpy(c.source(7)).cuda()
+    h = (2.0 * f - 0.5 * g).contiguous()
+    zin = torch.stack([f, g, h, torch.full_like(f, 3.75)]).contiguous()
+    zout = torch.empty((4,) + c.dst_shape, device="cuda", dtype=torch.float32)
+    assert ezb.ezsint_batch(zout, zin, 4) == 0
+    torch.cuda.synchronize()
+    rng = float((f.max() - f.min()).item())
+    lin = (2.0 * zout[0].double() - 0.5 * zout[1].double() - zout[2].double()).abs().max().item()
+    assert lin < 2e-5 * rng
+    assert (zout[3] - 3.75).abs().max().item() < 1e-5
+    one = torch.empty(c.dst_shape, device="cuda", dtype=torch.float32)
+    assert ezb.ezsint(one, g) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(one, zout[1])
+    x, y, zb, counts = ezb.get_gridset(c.gdout, c.gdin, c.n_out)
+    yang = int(counts[5])
+    assert 0.55 < yang / c.n_out < 0.70      # Yin's 270 x 90 degree core covers 37.5 % of an equal-angle lat-lon grid
