@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--levels", type=int, default=0, help="override the number of fields per step")
     ap.add_argument("--cpu-sample-levels", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--arith", type=int, default=1)
+    ap.add_argument("--arith", type=int, default=2)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +249,7 @@ def main():
     e_all1.record(stream)
     barrier()
     launches = B.launch_count()
+    path, nlist = B.last_path()
     total_ms = e_all0.elapsed_time(e_all1)
     step_ms = [a.elapsed_time(b) for a, b in evs]
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -291,7 +292,8 @@ def main():
     kern_ms = statistics.mean(step_ms)   # one step == one launch of the dominant kernel (+ its launch gap)
     achieved = abytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_kind": peak_kind, "kernel": "k_interp_fast<%s>" % {"nearest": 0, "linear": 1, "cubic": 3}[case.opts.get("interp_degree", "cubic")],
+                "peak_kind": peak_kind, "kernel": ("k_interp_tiled<%s>" if path & 2 else "k_interp_fast<%s>") % {"nearest": 0, "linear": 1, "cubic": 3}[case.opts.get("interp_degree", "cubic")],
+                "points_on_per_point_list": nlist,
                 "algorithmic_bytes_per_launch": abytes, "kernel_ms": kern_ms}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(traffic_file):

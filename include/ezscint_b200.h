@@ -106,13 +106,17 @@ int32_t c_ezsint_batch(float *zout, float *zin, int32_t nfields);
 int32_t c_ezuvint_batch(float *uuout, float *vvout, float *uuin, float *vvin, int32_t nfields);
 /* CUDA stream (cudaStream_t as void*) used by the calling thread's launches; NULL = default stream */
 int32_t c_ezb200_set_stream(void *stream);
-/* 0 = reference evaluation order (bit-parity), 1 = fp64 weight form (default); per calling thread */
+/* 0 = reference evaluation order (bit-parity), 1 = fp64 weight form, 2 = fp32 difference form with the
+   shared-memory tiled kernel where the target is a 2-D grid at least as fine as the source (default); per calling thread */
 int32_t c_ezb200_set_arith(int32_t mode);
 int32_t c_ezb200_get_arith(void);
 /* copy the cached gridset of (gdout, gdin) to host arrays (any may be NULL): x, y [npts], zone bits [npts], counts[6] */
 int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, uint8_t *zonebits, int32_t *counts);
 /* number of CUDA kernels launched by the calling thread since the last call with reset != 0 */
 int64_t c_ezb200_launch_count(int32_t reset);
+/* kernels used by the calling thread's last interpolation launch: bit 0 per-point kernel, bit 1 tiled kernel,
+   bit 2 per-point kernel on the compacted list of points the tiles leave out (*nlist = its length) */
+int32_t c_ezb200_last_path(int32_t *nlist);
 /* block until the calling thread's stream is idle ; returns 0 or -1 with the CUDA error on stderr */
 int32_t c_ezb200_sync(void);
 const char *c_ezb200_version(void);

@@ -92,6 +92,7 @@ class EzLib:
             L.c_ezb200_launch_count.argtypes = [_i32]
             L.c_ezb200_launch_count.restype = C.c_int64
             L.c_ezb200_version.restype = C.c_char_p
+            L.c_ezb200_last_path.argtypes = [C.POINTER(_i32)]
 
     # ---- descriptors -------------------------------------------------------------------------
     def cxgaig(self, grtyp, xg1, xg2, xg3, xg4):
@@ -232,6 +233,11 @@ class EzLib:
 
     def launch_count(self, reset=False):
         return self.lib.c_ezb200_launch_count(1 if reset else 0)
+
+    def last_path(self):
+        """(bitmask, nlist) of the kernels the last interpolation launch used: 1 per-point, 2 tiled, 4 per-point on the compacted list."""
+        n = _i32(0)
+        return self.lib.c_ezb200_last_path(C.byref(n)), n.value
 
     def sync(self):
         return self.lib.c_ezb200_sync()

@@ -43,7 +43,16 @@ struct Options {   // _groptions, ez_def.h:225-243 ; defaults ez_statics.c:17
     float valeur_extrap = 0.0f;
 };
 
+struct TilePlan {   // classification of the target points for the tiled kernel (ez_interp_tiled.cuh), per degree and zone setting
+    bool built = false, suitable = false;
+    TileDesc *d_tiles = nullptr;
+    uint32_t *d_flags = nullptr;
+    int *d_list = nullptr;
+    int nlist = 0, ntiles_fast = 0;
+};
+
 struct Gset {   // _gridset, ez_def.h:148-166, device-resident
+    TilePlan plans[4];          // [cubic ? 2 : 0) + use_zones]
     int gdin = -1;
     bool built = false;
     bool yy = false;            // source is a 'U' supergrid: zb carries the panel bit, no zones
@@ -98,8 +107,10 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     int gdin = -1, gdout = -1;
     Options opt;
     cudaStream_t stream = 0;
-    int arith = 1;
+    int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
+    int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 tiled, 4 per-point on the compacted list
+    int last_nlist = 0;
     DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4];
 };
 thread_local Session S;
@@ -611,7 +622,57 @@ Gset *ensure_gset(Grid &out, Grid &in) {
     return gs;
 }
 
+// Tile plan for the current (degree, zones) of `a` on this gridset; built on first use, kept in HBM.
+TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
+    TilePlan &tp = gs.plans[(a.o.degree == EZ_CUBIC ? 2 : 0) + (a.use_zones ? 1 : 0)];
+    if (tp.built) return &tp;
+    int ntx, nty;
+    ezk::tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
+    const size_t ntiles = (size_t)ntx * nty;
+    unsigned int *d_counters = (unsigned int *)S.st_misc[3].get(4 * sizeof(unsigned int));
+    if (!d_counters) return nullptr;
+    if (cudaMalloc((void **)&tp.d_tiles, ntiles * sizeof(TileDesc)) != cudaSuccess ||
+        cudaMalloc((void **)&tp.d_flags, ntiles * 8 * sizeof(uint32_t)) != cudaSuccess) {
+        fprintf(stderr, "<ezb200> cudaMalloc failed for the tile plan: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), S.stream);
+    ezk::tile_classify(a, tp.d_tiles, tp.d_flags, d_counters, S.stream);
+    S.launches++;
+    unsigned int hc[4] = {0, 0, 0, 0};
+    if (cudaMemcpyAsync(hc, d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+        cudaStreamSynchronize(S.stream) != cudaSuccess) {
+        fprintf(stderr, "<ezb200> tile classification failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    tp.nlist = (int)hc[0];
+    tp.ntiles_fast = (int)hc[1];
+    // the tile kernel pays off when most points take it (target as fine as the source); otherwise keep the per-point kernel
+    tp.suitable = tp.ntiles_fast > 0 && (size_t)tp.nlist * 2 <= (size_t)a.npts;
+    if (tp.suitable && tp.nlist > 0) {
+        if (cudaMalloc((void **)&tp.d_list, (size_t)tp.nlist * sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemsetAsync(d_counters, 0, sizeof(unsigned int), S.stream);
+        ezk::tile_list(a, tp.d_flags, tp.d_list, d_counters, S.stream);
+        S.launches++;
+    }
+    if (!tp.suitable) {
+        cudaFree(tp.d_tiles); cudaFree(tp.d_flags);
+        tp.d_tiles = nullptr; tp.d_flags = nullptr;
+    }
+    if (S.opt.verbose > 0)
+        fprintf(stderr, "<ezb200> tile plan: %d of %d points on the per-point list, %d of %zu tiles active, %s\n", tp.nlist, a.npts,
+                tp.ntiles_fast, ntiles, tp.suitable ? "tiled kernel" : "per-point kernel");
+    tp.built = true;
+    return &tp;
+}
+
 void free_gset(Gset &gs) {
+    for (auto &tp : gs.plans) {
+        if (tp.d_tiles) cudaFree(tp.d_tiles);
+        if (tp.d_flags) cudaFree(tp.d_flags);
+        if (tp.d_list) cudaFree(tp.d_list);
+        tp = TilePlan();
+    }
     if (gs.d_x) cudaFree(gs.d_x);
     if (gs.d_y) cudaFree(gs.d_y);
     if (gs.d_zb) cudaFree(gs.d_zb);
@@ -722,6 +783,20 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.fs = fs;
         }
     }
+    a.out_ni = out.ni;
+    a.out_nj = out.nj;
+    if (ezk::tiled_eligible(a)) {
+        TilePlan *tp = ensure_tileplan(*gs, a);
+        if (!tp) return -1;
+        if (tp->suitable) {
+            a.tiles = tp->d_tiles;
+            a.tile_flags = tp->d_flags;
+            a.list = tp->d_list;
+            a.nlist = tp->nlist;
+        }
+    }
+    S.last_path = a.tiles ? (2 | (a.nlist > 0 ? 4 : 0)) : 1;
+    S.last_nlist = a.tiles ? a.nlist : 0;
     S.launches += ezk::interp(a, S.stream);
     // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged
     if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
@@ -954,6 +1029,10 @@ int64_t c_ezb200_launch_count(int32_t reset) {
     int64_t v = S.launches;
     if (reset) S.launches = 0;
     return v;
+}
+int32_t c_ezb200_last_path(int32_t *nlist) {
+    if (nlist) *nlist = S.last_nlist;
+    return S.last_path;
 }
 int32_t c_ezb200_sync(void) {
     CUDA_OK(cudaStreamSynchronize(S.stream));

@@ -15,6 +15,7 @@
 //      weights evaluated once per point in fp64 and applied with fp64 FMAs per level.
 // Compiled with -fmad=false; the weight form uses explicit fma().
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math.h>
 #include "ez_kernels.h"
 
@@ -572,6 +573,7 @@ __global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj,
 }  // namespace
 
 #include "ez_interp_fast.cuh"
+#include "ez_interp_tiled.cuh"
 
 namespace ezk {
 
@@ -590,8 +592,53 @@ void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldSc
     k_field_scalars<<<(nt + 63) / 64, 64, 0, s>>>(a, need_poles, need_minmax, fs, scratch);
 }
 
+bool tiled_eligible(const InterpArgs &a) {
+    if (a.o.arith != 2 || (a.o.degree != EZ_LINEAR && a.o.degree != EZ_CUBIC)) return false;
+    if (a.out_ni < 2 || a.out_nj < 2) return false;
+    if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
+    if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
+    return true;
+}
+
+void tile_dims(int out_ni, int out_nj, int *ntx, int *nty) {
+    *ntx = (out_ni + TO - 1) / TO;
+    *nty = (out_nj + TO - 1) / TO;
+}
+
+void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *counters, cudaStream_t s) {
+    int ntx, nty;
+    tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
+    dim3 grid(ntx, nty);
+    if (a.o.degree == EZ_CUBIC) k_tile_classify<3><<<grid, TT * TT, 0, s>>>(a, tiles, flags, counters);
+    else k_tile_classify<1><<<grid, TT * TT, 0, s>>>(a, tiles, flags, counters);
+}
+
+void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s) {
+    int ntx, nty;
+    tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
+    dim3 grid(ntx, nty);
+    k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor);
+}
+
 int interp(const InterpArgs &a, cudaStream_t s) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
+    if (a.tiles) {
+        // tiled path: the tile kernel for every point that fits, the per-point kernel for the compacted rest
+        int ntx, nty, launches = 1;
+        tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
+        dim3 grid(ntx, nty);
+        const size_t smem = 2 * TILE_CAP * sizeof(float);
+        if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, TT * TT, smem, s>>>(a);
+        else k_interp_tiled<1><<<grid, TT * TT, smem, s>>>(a);
+        if (a.nlist > 0) {
+            InterpArgs b = a;
+            b.tiles = nullptr;
+            b.tile_flags = nullptr;
+            launch_fast(b, s);
+            launches++;
+        }
+        return launches;
+    }
     if (a.o.arith >= 1 && launch_fast(a, s)) return 1;
     int nb = (a.npts + TPB - 1) / TPB;
     k_interp_ref<<<nb, TPB, 0, s>>>(a);

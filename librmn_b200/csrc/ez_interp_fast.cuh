@@ -225,7 +225,30 @@ __device__ __forceinline__ float eval_linear(const PlanLin &p, const float *__re
     return (float)zlin(y2, y3, p.dy);
 }
 
-// DEG = 0 nearest, 1 linear, 3 cubic (fp64 weight form), 4 cubic (fp32 difference form).  Requires plain field access (no hemispheric mirror, no y inversion).
+// fp32 difference form of the bilinear interpolant about z00 (arith = 2): the four weights sum to exactly one,
+// so zo = z00 + w10 (z10 - z00) + w01 (z01 - z00) + w11 (z11 - z00) with fp64-derived weights.
+struct PlanLinF {
+    int o00, o10, o01, o11;
+    float w10, w01, w11;
+};
+__device__ __forceinline__ PlanLinF to_f32(const PlanLin &p) {
+    PlanLinF q;
+    q.o00 = p.o00; q.o10 = p.o10; q.o01 = p.o01; q.o11 = p.o11;
+    q.w10 = (float)(p.dx * (1.0 - p.dy));
+    q.w01 = (float)((1.0 - p.dx) * p.dy);
+    q.w11 = (float)(p.dx * p.dy);
+    return q;
+}
+__device__ __forceinline__ float eval_linear_f32(const PlanLinF &p, const float *__restrict__ z) {
+    const float z00 = __ldg(z + p.o00), z10 = __ldg(z + p.o10), z01 = __ldg(z + p.o01), z11 = __ldg(z + p.o11);
+    float acc = p.w10 * (z10 - z00);
+    acc = fmaf(p.w01, z01 - z00, acc);
+    acc = fmaf(p.w11, z11 - z00, acc);
+    return z00 + acc;
+}
+
+// DEG = 0 nearest, 1 linear (fp64, reference order), 3 cubic (fp64 weight form), 4 cubic (fp32 difference form),
+// 5 linear (fp32 difference form).  Requires plain field access (no hemispheric mirror, no y inversion).
 // The grid descriptor is taken by reference straight from kernel-parameter (constant-bank) space: the Yin/Yang
 // choice is a branch around two instantiations rather than a pointer select, which would force a local copy.
 template <int DEG>
@@ -247,6 +270,10 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
             const PlanCub p = plan_cubic(g, px, py);
 #pragma unroll 2
             for (int f = 0; f < nf; f++) zo[f * os] = eval_cubic(p, z + f * is);
+        } else if (DEG == 5) {
+            const PlanLinF p = to_f32(plan_linear(g, px, py));
+#pragma unroll 4
+            for (int f = 0; f < nf; f++) zo[f * os] = eval_linear_f32(p, z + f * is);
         } else {
             const PlanCubF p = to_f32(plan_cubic(g, px, py));
 #pragma unroll 2
@@ -265,8 +292,10 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
 
 template <int DEG>
 __global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ InterpArgs a) {
-    const int n = blockIdx.x * TPB + threadIdx.x;
-    if (n >= a.npts) return;
+    // with an index list (the points the tile kernel leaves out) thread t owns target point list[t]
+    const int t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= (a.list ? a.nlist : a.npts)) return;
+    const int n = a.list ? a.list[t] : t;
     const float px = a.x[n], py = a.y[n];
     const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
     const uint8_t zbits = a.use_zones ? (uint8_t)(bits & 0x1f) : (uint8_t)0;
@@ -279,10 +308,14 @@ __global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ Int
 bool launch_fast(const InterpArgs &a, cudaStream_t s) {
     if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
     if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
-    const int nb = (a.npts + TPB - 1) / TPB;
+    const int nb = ((a.list ? a.nlist : a.npts) + TPB - 1) / TPB;
+    if (nb <= 0) return true;
     switch (a.o.degree) {
         case EZ_NEAREST: k_interp_fast<0><<<nb, TPB, 0, s>>>(a); return true;
-        case EZ_LINEAR: k_interp_fast<1><<<nb, TPB, 0, s>>>(a); return true;
+        case EZ_LINEAR:
+            if (a.o.arith == 2) k_interp_fast<5><<<nb, TPB, 0, s>>>(a);
+            else k_interp_fast<1><<<nb, TPB, 0, s>>>(a);
+            return true;
         case EZ_CUBIC:
             if (a.o.arith == 2) k_interp_fast<4><<<nb, TPB, 0, s>>>(a);
             else k_interp_fast<3><<<nb, TPB, 0, s>>>(a);

@@ -1,0 +1,284 @@
+// librmn_b200/csrc/ez_interp_tiled.cuh -- the shared-memory tiled, register-blocked gather kernel
+// (linear and cubic, "arith = 2" fp32 difference form).  Included by ez_interp.cu after ez_interp_fast.cuh.
+//
+// Why: the one-thread-per-point kernel issues 16 scalar gathers per point and level; ncu shows it at
+// ~2.5 L1 wavefronts per gather and 61 % of the L1 wavefront rate while HBM sits at 8 % (profiles/r1a_*).
+// The L1/LSU path, not HBM, is the wall.  This kernel removes most of that traffic:
+//   * a CTA owns a 32 x 32 tile of TARGET points; the bounding box of all their stencils in the source
+//     level (a few KB: the tile's footprint) is staged in shared memory by cp.async, double-buffered
+//     across levels, so global memory is read in whole rows (coalesced) exactly once per tile and level;
+//   * a thread owns a 2 x 2 block of target points.  When the target grid is as fine as or finer than the
+//     source (every configuration of BASELINE.json), the four 4x4 stencils fit one 5 x 5 window: 25
+//     conflict-free LDS feed 4 outputs (6.25 loads per output instead of 16).  Each output applies its
+//     own weights zero-padded to the window (wx'[5], wy'[5]); no selects, no dynamic register indexing;
+//   * the arithmetic is the fp32 difference form of ez_interp_fast.cuh taken about the window centre:
+//     zo = zc (1 + s) + sum_r wy'_r sum_c wx'_c (z_rc - zc), weights from the fp64 plan.
+// Points that do not fit (zone points, the longitudinal seam, Yin/Yang panel borders, windows larger than
+// 5 x 5) are classified ONCE per (gridset, degree) by k_tile_classify into a compacted list and handled by
+// the per-point kernel (k_interp_fast with an index list); the tile kernel never branches on them.
+#pragma once
+#include <cuda_pipeline_primitives.h>
+
+namespace {
+
+constexpr int TT = 16;             // threads per tile side
+constexpr int TO = 2 * TT;         // target points per tile side
+constexpr int TILE_CAP = 2560;     // floats per shared-memory buffer (two buffers per CTA)
+
+template <int DEG> struct Sten {
+    static constexpr int S = (DEG == 3) ? 4 : 2;   // stencil width
+    static constexpr int W = S + 1;                // window width of a 2 x 2 block
+};
+
+// stencil origin (0-based column of the first stencil column, 0-based row of the first stencil row in the
+// stored field) and the per-axis weights of one target point.  ok = the stencil columns are contiguous.
+template <int DEG>
+__device__ __forceinline__ bool point_plan(const GridDev &g, float px, float py, int &c0, int &r0, float wx[4], float wy[4], float &sm1) {
+    if (DEG == 3) {
+        const PlanCub p = plan_cubic(g, px, py);
+        c0 = p.c[0];
+        r0 = p.r0 / p.ni;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { wx[k] = (float)p.wx[k]; wy[k] = (float)p.wy[k]; }
+        sm1 = (float)((p.wx[0] + p.wx[1] + p.wx[2] + p.wx[3]) * (p.wy[0] + p.wy[1] + p.wy[2] + p.wy[3]) - 1.0);
+        return p.c[1] == c0 + 1 && p.c[2] == c0 + 2 && p.c[3] == c0 + 3;
+    } else {
+        const PlanLin p = plan_linear(g, px, py);
+        r0 = p.o00 / g.ni;
+        c0 = p.o00 - r0 * g.ni;
+        wx[0] = (float)(1.0 - p.dx); wx[1] = (float)p.dx; wx[2] = wx[3] = 0.f;
+        wy[0] = (float)(1.0 - p.dy); wy[1] = (float)p.dy; wy[2] = wy[3] = 0.f;
+        sm1 = 0.f;
+        return p.o10 == p.o00 + 1;
+    }
+}
+
+// the four target points of a thread: (ox, oy), (ox+1, oy), (ox, oy+1), (ox+1, oy+1)
+struct Quad {
+    int ox, oy;
+    __device__ __forceinline__ bool valid(int p, int ni, int nj) const { return (ox + (p & 1)) < ni && (oy + (p >> 1)) < nj; }
+    __device__ __forceinline__ int index(int p, int ni) const { return (oy + (p >> 1)) * ni + ox + (p & 1); }
+};
+// both polar caps (the rows that carry zone points and ragged work) are scheduled first: 0, last, 1, last-1 ...
+__device__ __forceinline__ int remap_tile_row(int by, int nty) { return (by & 1) ? (nty - 1 - (by >> 1)) : (by >> 1); }
+__device__ __forceinline__ Quad quad_of_thread(int bx, int by) {
+    Quad q;
+    q.ox = bx * TO + 2 * (threadIdx.x & (TT - 1));
+    q.oy = by * TO + 2 * (threadIdx.x >> 4);
+    return q;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// classification (once per gridset, degree and zone setting)
+// ---------------------------------------------------------------------------------------------------
+template <int DEG>
+__device__ __forceinline__ void classify_thread(const GridDev &g, const InterpArgs &a, const Quad &q, int tile_panel, bool &fast, int &wc0, int &wr0) {
+    const int ni = a.out_ni, nj = a.out_nj;
+    int cmin = INT_MAX, cmax = INT_MIN, rmin = INT_MAX, rmax = INT_MIN, nvalid = 0;
+    bool ok = true;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        if (!q.valid(p, ni, nj)) continue;
+        nvalid++;
+        const int n = q.index(p, ni);
+        const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
+        const int panel = (a.yy && (bits & ZB_YANG)) ? 1 : 0;
+        if ((a.use_zones && (bits & 0x1f)) || panel != tile_panel) { ok = false; continue; }
+        int c0, r0;
+        float wx[4], wy[4], s;
+        if (!point_plan<DEG>(g, a.x[n], a.y[n], c0, r0, wx, wy, s)) ok = false;
+        cmin = min(cmin, c0); cmax = max(cmax, c0);
+        rmin = min(rmin, r0); rmax = max(rmax, r0);
+    }
+    fast = ok && nvalid > 0 && (cmax - cmin) <= 1 && (rmax - rmin) <= 1;
+    wc0 = cmin;
+    wr0 = rmin;
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant__ InterpArgs a, TileDesc *__restrict__ tiles,
+                                                           uint32_t *__restrict__ flags, unsigned int *__restrict__ counters) {
+    __shared__ int s_box[4];
+    __shared__ int s_cnt[2];
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const Quad q = quad_of_thread(blockIdx.x, blockIdx.y);
+    const int ni = a.out_ni, nj = a.out_nj;
+    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_cnt[0] = 0; s_cnt[1] = 0; }
+    // panel of the tile: majority of the threads' first points
+    const bool v0 = q.valid(0, ni, nj);
+    const bool yang0 = v0 && a.yy && a.zb && (a.zb[q.index(0, ni)] & ZB_YANG);
+    const int n_valid = __syncthreads_count(v0);
+    const int n_yang = __syncthreads_count(yang0);
+    const int tile_panel = (2 * n_yang > n_valid) ? 1 : 0;
+    bool fast;
+    int wc0, wr0;
+    if (tile_panel) classify_thread<DEG>(a.src2, a, q, 1, fast, wc0, wr0);
+    else classify_thread<DEG>(a.src, a, q, 0, fast, wc0, wr0);
+    if (fast) {
+        atomicMin(&s_box[0], wc0); atomicMin(&s_box[1], wr0);
+        atomicMax(&s_box[2], wc0 + Sten<DEG>::W - 1); atomicMax(&s_box[3], wr0 + Sten<DEG>::W - 1);
+    }
+    __syncthreads();
+    const int c0 = s_box[0], r0 = s_box[1], c1 = s_box[2], r1 = s_box[3];
+    // the box holds every fast thread's full window; a window may overhang the field by one column/row on the
+    // high side (that column/row carries zero weights) -- stage_tile replicates the field edge there
+    const int w = c1 - c0 + 1, h = r1 - r0 + 1;
+    const bool box_ok = (c0 != INT_MAX) && (long)(w | 1) * h <= TILE_CAP;
+    fast = fast && box_ok;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, fast);
+    if ((threadIdx.x & 31) == 0) flags[tile * 8 + (threadIdx.x >> 5)] = ballot;
+    int nslow = 0;
+    if (!fast)
+        for (int p = 0; p < 4; p++) nslow += q.valid(p, ni, nj) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) nslow += __shfl_xor_sync(0xffffffffu, nslow, o);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], nslow); atomicAdd(&s_cnt[1], __popc(ballot)); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TileDesc td;
+        td.c0 = box_ok ? c0 : 0; td.r0 = box_ok ? r0 : 0; td.w = box_ok ? w : 0; td.h = box_ok ? h : 0;
+        td.panel = tile_panel; td.nfast = s_cnt[1]; td.nslow = s_cnt[0]; td.pad = 0;
+        tiles[tile] = td;
+        atomicAdd(counters + 0, (unsigned int)s_cnt[0]);
+        if (s_cnt[1] > 0) atomicAdd(counters + 1, 1u);
+    }
+}
+
+// second pass: the points the tile kernel leaves out, compacted (warp-aggregated append; order is irrelevant)
+__global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ InterpArgs a, const uint32_t *__restrict__ flags,
+                                                       int *__restrict__ list, unsigned int *__restrict__ cursor) {
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const Quad q = quad_of_thread(blockIdx.x, blockIdx.y);
+    const int ni = a.out_ni, nj = a.out_nj;
+    const bool fast = (flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
+    int k = 0;
+    if (!fast)
+        for (int p = 0; p < 4; p++) k += q.valid(p, ni, nj) ? 1 : 0;
+    int incl = k;
+    const int lane = threadIdx.x & 31;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned int base = 0;
+    if (lane == 0 && total > 0) base = atomicAdd(cursor, (unsigned int)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (k > 0) {
+        unsigned int at = base + (unsigned int)(incl - k);
+        for (int p = 0; p < 4; p++)
+            if (q.valid(p, ni, nj)) list[at++] = q.index(p, ni);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_tile(float *__restrict__ buf, const float *__restrict__ zf, const TileDesc &td, int src_ni, int src_rows,
+                                           int pitch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < td.h; r += (TT * TT) / 32) {
+        const float *src = zf + (long)min(td.r0 + r, src_rows - 1) * src_ni;
+        float *dst = buf + r * pitch;
+        for (int c = lane; c < td.w; c += 32) __pipeline_memcpy_async(dst + c, src + min(td.c0 + c, src_ni - 1), 4);
+    }
+    __pipeline_commit();
+}
+
+template <int DEG>
+__device__ __forceinline__ void tiled_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ zin, const TileDesc &td,
+                                           const Quad &q, bool fast, float *__restrict__ smem) {
+    constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
+    const int ni = a.out_ni, nj = a.out_nj;
+    const int pitch = td.w | 1;
+    float wx[4][W], wy[4][W], sm1[4];
+    bool valid[4];
+    int base = 0;
+    if (fast) {
+        int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
+        float tx[4][4], ty[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            valid[p] = q.valid(p, ni, nj);
+            c0[p] = INT_MAX; r0[p] = INT_MAX; sm1[p] = 0.f;
+            if (valid[p]) {
+                const int n = q.index(p, ni);
+                point_plan<DEG>(g, a.x[n], a.y[n], c0[p], r0[p], tx[p], ty[p], sm1[p]);
+                wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const bool sx = valid[p] && (c0[p] != wc0), sy = valid[p] && (r0[p] != wr0);   // offset 0 or 1 inside the window
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const float lo = (k < S) ? tx[p][k] : 0.f, hi = (k > 0) ? tx[p][k - 1] : 0.f;
+                wx[p][k] = valid[p] ? (sx ? hi : lo) : 0.f;
+                const float lo2 = (k < S) ? ty[p][k] : 0.f, hi2 = (k > 0) ? ty[p][k - 1] : 0.f;
+                wy[p][k] = valid[p] ? (sy ? hi2 : lo2) : 0.f;
+            }
+        }
+        base = (wr0 - td.r0) * pitch + (wc0 - td.c0);
+    }
+    const int src_rows = g.j2 - g.j1 + 1;
+    const int nf = a.nfields;
+    const long is = a.in_stride, os = a.out_stride;
+    const bool vec2 = ((ni & 1) == 0);   // float2 stores are 8-byte aligned iff the target row length is even
+    float *o0 = a.zout + (long)q.oy * ni + q.ox;
+    float *o1 = o0 + ni;
+    stage_tile(smem, zin, td, g.ni, src_rows, pitch);
+    for (int f = 0; f < nf; f++) {
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        if (f + 1 < nf) stage_tile(smem + ((f + 1) & 1) * TILE_CAP, zin + (long)(f + 1) * is, td, g.ni, src_rows, pitch);
+        if (fast) {
+            const float *s = smem + (f & 1) * TILE_CAP + base;
+            float d[W][W];
+#pragma unroll
+            for (int r = 0; r < W; r++)
+#pragma unroll
+                for (int c = 0; c < W; c++) d[r][c] = s[r * pitch + c];
+            const float zc = d[W / 2][W / 2];
+#pragma unroll
+            for (int r = 0; r < W; r++)
+#pragma unroll
+                for (int c = 0; c < W; c++) d[r][c] = d[r][c] - zc;
+            float res[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int r = 0; r < W; r++) {
+                    float rs = wx[p][0] * d[r][0];
+#pragma unroll
+                    for (int c = 1; c < W; c++) rs = fmaf(wx[p][c], d[r][c], rs);
+                    acc = fmaf(wy[p][r], rs, acc);
+                }
+                res[p] = zc + fmaf(zc, sm1[p], acc);
+            }
+            if (vec2 && valid[1]) {
+                *reinterpret_cast<float2 *>(o0 + f * os) = make_float2(res[0], res[1]);
+                if (valid[2]) *reinterpret_cast<float2 *>(o1 + f * os) = make_float2(res[2], res[3]);
+            } else {
+                if (valid[0]) o0[f * os] = res[0];
+                if (valid[1]) o0[f * os + 1] = res[1];
+                if (valid[2]) o1[f * os] = res[2];
+                if (valid[3]) o1[f * os + 1] = res[3];
+            }
+        }
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(TT * TT) k_interp_tiled(const __grid_constant__ InterpArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int by = remap_tile_row(blockIdx.y, gridDim.y);
+    const int tile = by * gridDim.x + blockIdx.x;
+    const TileDesc td = a.tiles[tile];
+    if (td.nfast == 0) return;
+    const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
+    const Quad q = quad_of_thread(blockIdx.x, by);
+    if (td.panel) tiled_body<DEG>(a.src2, a, a.zin + a.panel_stride, td, q, fast, smem);
+    else tiled_body<DEG>(a.src, a, a.zin, td, q, fast, smem);
+}
+
+}  // namespace

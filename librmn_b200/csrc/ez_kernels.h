@@ -21,6 +21,13 @@ struct InterpArgs {
     int npts;
     InterpOpts o;
     const FieldScalars *fs; // device per-field scalars (pole means, fudge) or nullptr
+    // tiled kernel (ez_interp_tiled.cuh): target grid shape, per-tile descriptors and thread masks
+    int out_ni, out_nj;
+    const TileDesc *tiles;
+    const uint32_t *tile_flags;   // 8 words per tile: bit t = thread t takes the tile path
+    // per-point kernel restricted to a compacted list of target points (nullptr = all npts points)
+    const int *list;
+    int nlist;
 };
 
 struct WindArgs {
@@ -49,6 +56,11 @@ void ll2xy_points(const GridDev &g, int njs, const float *lat, const float *lon,
 void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s);
 // K0-K9: the gather-interpolation kernel.  Returns the number of kernel launches issued.
 int interp(const InterpArgs &a, cudaStream_t s);
+// tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry
+bool tiled_eligible(const InterpArgs &a);
+void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
+void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *counters, cudaStream_t s);
+void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s);
 // K19 integer mask transfer
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,
                    int linear, cudaStream_t s);

@@ -53,3 +53,10 @@ struct InterpOpts {
 struct FieldScalars {
     float pole_n, pole_s, fudge, pad;
 };
+
+// One 32 x 32 tile of target points for the tiled gather kernel (ez_interp_tiled.cuh): the box of the source
+// field its fast threads read (first column/row, width, height), the Yin-Yang panel it reads from, and counts.
+struct TileDesc {
+    int c0, r0, w, h;
+    int panel, nfast, nslow, pad;
+};

@@ -182,7 +182,7 @@ def test_values_against_oracle(ezb, ezref, cuda_ok, degree, arith):
             assert flipped <= max(4, 0.02 * out_b.size), "%s: too many flipped near ties (%d)" % (c_b.name, flipped)
             print("%-44s a%d rc=%d max|d|/range=%.2e bit-diff=%d/%d flipped-ties=%d" % (c_b.name, arith, rc_b, mx, nbit, out_b.size, flipped))
     finally:
-        ezb.set_arith(1)
+        ezb.set_arith(2)
 
 
 @pytest.mark.parametrize("degree", cases.DEGREES)
@@ -267,6 +267,77 @@ def test_mask_transfer_matches_oracle(ezb, ezref, cuda_ok):
 
 
 # ---------------------------------------------------------------------------------------------------
+# the shared-memory tiled kernel (arith = 2, the default) at sizes where whole tiles take it
+# ---------------------------------------------------------------------------------------------------
+def medium_cases(lib, degree):
+    cs = [
+        configs.c1(lib, n=416, degree=degree),                         # L -> N, 5x finer target, wrap-2 seam through the tiles
+        configs.c2(lib, res_src=0.6, res_dst=0.4, degree=degree),      # Yin-Yang: both panels, panel borders inside tiles
+        configs.c5(lib, res_src=0.6, res_dst=0.4, degree=degree),      # global Z: seam + both polar caps
+        configs.c3(lib, scale=4, degree=degree),                       # rotated LAM, winds, ~10 % DEHORS
+    ]
+    c = configs.c3(lib, scale=4, degree=degree, extrap="value")
+    c.vector = False
+    c.name += "_scalar_value"
+    c.opts["extrap_value"] = -5.0
+    cs.append(c)
+    return cs
+
+
+@pytest.mark.parametrize("degree", ["linear", "cubic"])
+def test_tiled_kernel_against_oracle(ezb, ezref, cuda_ok, degree):
+    ezb.set_arith(2)
+    for c_b, c_r in zip(medium_cases(ezb, degree), medium_cases(ezref, degree)):
+        rc_b, out_b = cases.run_case(ezb, c_b)
+        path, nlist = ezb.last_path()
+        assert path & 2, "%s did not take the tiled kernel (path=%d)" % (c_b.name, path)
+        assert nlist < 0.35 * c_b.n_out, "%s: %d of %d points left to the per-point list" % (c_b.name, nlist, c_b.n_out)
+        rc_r, out_r = cases.run_case(ezref, c_r)
+        assert rc_b == rc_r, c_b.name
+        rng = cases.field_range(c_b)
+        if c_b.name.startswith("C2"):
+            tie = None
+        else:
+            xr, yr = oracle_xy(ezref, c_r)
+            ex, ey = coord_eps(c_b, xr, yr)
+            tie = (near_half(xr, ex) | near_half(yr, ey)) & ((xr < 1.5) | (yr < 1.5) | (xr > c_b.src_shape[1] - 0.5) | (yr > c_b.src_shape[0] - 0.5))
+            tie |= near_int(yr, ey) & ((yr < 2.5) | (yr > c_b.src_shape[0] - 2.5))
+            tie = np.broadcast_to(tie.reshape(c_b.dst_shape), out_b.shape)
+        mx, nbit, flipped = compare(c_b.name + " tiled", out_b, out_r, rng, tie)
+        assert flipped <= max(4, 0.01 * out_b.size), c_b.name
+        print("%-44s tiled rc=%d list=%d/%d max|d|/range=%.2e flipped-ties=%d" % (c_b.name, rc_b, nlist, c_b.n_out, mx, flipped))
+
+
+@pytest.mark.parametrize("degree", ["linear", "cubic"])
+def test_tiled_kernel_equals_per_point_kernel(ezb, cuda_ok, degree):
+    """Same plans, same fp32 difference form about a different centre: the tiled and the per-point kernels agree to
+    a few fp32 ulp of the local variation, on odd target shapes (ragged last tile row/column, unaligned rows)."""
+    import torch
+    for (ni, nj) in ((333, 201), (64, 64), (97, 33)):
+        gdin = configs.def_L(ezb, 360, 181, -90.0, 0.0, 1.0, 1.0)
+        gdout = configs.def_L(ezb, ni, nj, -60.0, 10.0, min(0.7, 60.0 / nj), min(0.7, 120.0 / ni))
+        c = configs.Case("odd", ezb)
+        c.opts = {"interp_degree": degree}
+        c.apply_options()
+        assert ezb.ezdefset(gdout, gdin) == 1
+        zin = torch.from_numpy(configs.field(*np.meshgrid(np.arange(181) - 90.0, np.arange(360.0), indexing="ij"), k=3)).cuda().contiguous()
+        nf = 3
+        zin = torch.stack([zin + k for k in range(nf)]).contiguous()
+        outs = []
+        for arith in (2, 1):
+            ezb.set_arith(arith)
+            z = torch.full((nf, nj, ni), -1.0, device="cuda", dtype=torch.float32)
+            assert ezb.ezsint_batch(z, zin, nf) >= 0
+            torch.cuda.synchronize()
+            if arith == 2:
+                assert ezb.last_path()[0] & 2
+            outs.append(z)
+        ezb.set_arith(2)
+        rng = float((zin[0].max() - zin[0].min()).item())
+        assert (outs[0].double() - outs[1].double()).abs().max().item() < 2e-6 * rng, (ni, nj)
+
+
+# ---------------------------------------------------------------------------------------------------
 # API-level consistency of the CUDA path with itself
 # ---------------------------------------------------------------------------------------------------
 def test_batch_call_equals_single_calls(ezb, cuda_ok):
@@ -333,7 +404,7 @@ def test_coincident_nodes_reproduce_samples_exactly(ezb, cuda_ok, degree, arith)
         assert ezb.ezsint(zout, zin) == 0
         torch.cuda.synchronize()
     finally:
-        ezb.set_arith(1)
+        ezb.set_arith(2)
     x, y, zb, counts = ezb.get_gridset(gdout, gdin, zout.numel())
     assert np.array_equal(x, np.round(x)) and np.array_equal(y, np.round(y)) and not counts[:5].any()
     assert torch.equal(zout, zin[40:681:2, 0:1440:2])
