@@ -256,5 +256,5 @@ def load(build_if_missing=False):
         if build_if_missing and not os.path.exists(LIB_PATH):
             from . import build as _b
             _b.build()
-        _lib = EzLib(LIB_PATH)
+        _lib = EzLib(os.environ.get("EZB200_LIB", LIB_PATH))   # EZB200_LIB: experiment builds (librmn_b200/build.py --out=...)
     return _lib

@@ -30,7 +30,12 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: experiment builds (e.g. defines=["EZ_NSTAGE=3"], out="libezb200_s3.so"), selected at run time with EZB200_LIB."""
+    global OUT
+    if out:
+        OUT = os.path.join(HERE, out)
+        force = True
     if not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -40,7 +45,10 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if out:
+            obj = obj.replace(".o", "." + out + ".o")
+            objs[-1] = obj
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
@@ -59,4 +67,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -627,9 +627,15 @@ int interp(const InterpArgs &a, cudaStream_t s) {
         int ntx, nty, launches = 1;
         tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
         dim3 grid(ntx, nty);
-        const size_t smem = 2 * TILE_CAP * sizeof(float);
-        if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, TT * TT, smem, s>>>(a);
-        else k_interp_tiled<1><<<grid, TT * TT, smem, s>>>(a);
+        const size_t smem = NSTAGE * TILE_CAP * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set && smem > 48 * 1024) {
+            cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
+        else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
         if (a.nlist > 0) {
             InterpArgs b = a;
             b.tiles = nullptr;

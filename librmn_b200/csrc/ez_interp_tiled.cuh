@@ -23,7 +23,17 @@ namespace {
 
 constexpr int TT = 16;             // threads per tile side
 constexpr int TO = 2 * TT;         // target points per tile side
-constexpr int TILE_CAP = 2560;     // floats per shared-memory buffer (two buffers per CTA)
+#ifndef EZ_TILE_CAP
+#define EZ_TILE_CAP 2560
+#endif
+#ifndef EZ_NSTAGE
+#define EZ_NSTAGE 4
+#endif
+#ifndef EZ_TILED_MINB
+#define EZ_TILED_MINB 3
+#endif
+constexpr int TILE_CAP = EZ_TILE_CAP;     // floats per shared-memory buffer
+constexpr int NSTAGE = EZ_NSTAGE;          // buffers per CTA: the producer warp runs NSTAGE-1 source levels ahead of the compute warps
 
 template <int DEG> struct Sten {
     static constexpr int S = (DEG == 3) ? 4 : 2;   // stencil width
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     // the box holds every fast thread's full window; a window may overhang the field by one column/row on the
     // high side (that column/row carries zero weights) -- stage_tile replicates the field edge there
     const int w = c1 - c0 + 1, h = r1 - r0 + 1;
-    const bool box_ok = (c0 != INT_MAX) && (long)(w | 1) * h <= TILE_CAP;
+    const bool box_ok = (c0 != INT_MAX) && w <= 64 && (long)(w | 1) * h <= TILE_CAP;
     fast = fast && box_ok;
     const unsigned int ballot = __ballot_sync(0xffffffffu, fast);
     if ((threadIdx.x & 31) == 0) flags[tile * 8 + (threadIdx.x >> 5)] = ballot;
@@ -173,25 +183,59 @@ __global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ I
 // ---------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_tile(float *__restrict__ buf, const float *__restrict__ zf, const TileDesc &td, int src_ni, int src_rows,
-                                           int pitch) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < td.h; r += (TT * TT) / 32) {
-        const float *src = zf + (long)min(td.r0 + r, src_rows - 1) * src_ni;
-        float *dst = buf + r * pitch;
-        for (int c = lane; c < td.w; c += 32) __pipeline_memcpy_async(dst + c, src + min(td.c0 + c, src_ni - 1), 4);
+// CTA-wide barrier shared by the producer warp and the compute warps (they reach it from different code paths)
+constexpr int NTHR_TILED = TT * TT + 32;
+__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR_TILED) : "memory"); }
+
+// The producer warp: stages the tile's box of every source level into shared memory with cp.async (LDGSTS), one
+// level ahead of the compute warps.  Lane l copies box columns l and l+32 (boxes are at most 64 wide) of every box
+// row; per row that is two predicated 4-byte copies and two pointer bumps.  Box cells that overhang the field (a
+// window may stick out by one zero-weight row/column on the high side) are never written and keep the zero fill.
+__device__ __forceinline__ void stage_level(float *__restrict__ dst, const float *__restrict__ src, int nrow, int src_ni, int pitch, bool c0ok,
+                                            bool c1ok) {
+#pragma unroll 4
+    for (int r = 0; r < nrow; r++) {
+        if (c0ok) __pipeline_memcpy_async(dst, src, 4);
+        if (c1ok) __pipeline_memcpy_async(dst + 32, src + 32, 4);
+        src += src_ni;
+        dst += pitch;
     }
     __pipeline_commit();
 }
 
+__device__ __forceinline__ void producer_warp(const InterpArgs &a, const float *__restrict__ zin, const TileDesc &td, int src_ni, int src_rows,
+                                              float *__restrict__ smem) {
+    const int lane = threadIdx.x & 31;
+    const int pitch = td.w | 1;
+    const int nrow = min(td.h, src_rows - td.r0);
+    const bool c0ok = lane < td.w && (td.c0 + lane) < src_ni;
+    const bool c1ok = (lane + 32) < td.w && (td.c0 + lane + 32) < src_ni;
+    const float *src = zin + (long)td.r0 * src_ni + td.c0 + lane;
+    const int nf = a.nfields;
+    const long is = a.in_stride;
+    // prologue: levels 0 .. NSTAGE-2 in flight (empty commit groups keep the group count uniform when nf is small)
+#pragma unroll
+    for (int k = 0; k < NSTAGE - 1; k++) {
+        if (k < nf) stage_level(smem + k * TILE_CAP + lane, src + k * is, nrow, src_ni, pitch, c0ok, c1ok);
+        else __pipeline_commit();
+    }
+    for (int f = 0; f < nf; f++) {
+        __pipeline_wait_prior(NSTAGE - 2);   // level f has landed
+        tile_barrier();                      // ... and every compute warp is done with level f-1, whose buffer is refilled next
+        const int nxt = f + NSTAGE - 1;
+        if (nxt < nf) stage_level(smem + (nxt % NSTAGE) * TILE_CAP + lane, src + nxt * is, nrow, src_ni, pitch, c0ok, c1ok);
+        else __pipeline_commit();
+    }
+}
+
 template <int DEG>
-__device__ __forceinline__ void tiled_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ zin, const TileDesc &td,
-                                           const Quad &q, bool fast, float *__restrict__ smem) {
+__device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs &a, const TileDesc &td, const Quad &q, bool fast,
+                                              const float *__restrict__ smem) {
     constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
     const int ni = a.out_ni, nj = a.out_nj;
     const int pitch = td.w | 1;
     float wx[4][W], wy[4][W], sm1[4];
-    bool valid[4];
+    bool valid[4] = {false, false, false, false};
     int base = 0;
     if (fast) {
         int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
@@ -219,19 +263,15 @@ __device__ __forceinline__ void tiled_body(const GridDev &g, const InterpArgs &a
         }
         base = (wr0 - td.r0) * pitch + (wc0 - td.c0);
     }
-    const int src_rows = g.j2 - g.j1 + 1;
     const int nf = a.nfields;
-    const long is = a.in_stride, os = a.out_stride;
-    const bool vec2 = ((ni & 1) == 0);   // float2 stores are 8-byte aligned iff the target row length is even
-    float *o0 = a.zout + (long)q.oy * ni + q.ox;
-    float *o1 = o0 + ni;
-    stage_tile(smem, zin, td, g.ni, src_rows, pitch);
+    const long os = a.out_stride;
+    // float2 stores need all four points and 8-byte alignment (even target row length; q.ox is even)
+    const bool full = fast && ((ni & 1) == 0) && valid[3] && ((reinterpret_cast<uintptr_t>(a.zout) & 7) == 0) && ((os & 1) == 0);
+    float *w0 = a.zout + (long)q.oy * ni + q.ox;
     for (int f = 0; f < nf; f++) {
-        __pipeline_wait_prior(0);
-        __syncthreads();
-        if (f + 1 < nf) stage_tile(smem + ((f + 1) & 1) * TILE_CAP, zin + (long)(f + 1) * is, td, g.ni, src_rows, pitch);
+        tile_barrier();
         if (fast) {
-            const float *s = smem + (f & 1) * TILE_CAP + base;
+            const float *s = smem + (f % NSTAGE) * TILE_CAP + base;
             float d[W][W];
 #pragma unroll
             for (int r = 0; r < W; r++)
@@ -255,30 +295,39 @@ __device__ __forceinline__ void tiled_body(const GridDev &g, const InterpArgs &a
                 }
                 res[p] = zc + fmaf(zc, sm1[p], acc);
             }
-            if (vec2 && valid[1]) {
-                *reinterpret_cast<float2 *>(o0 + f * os) = make_float2(res[0], res[1]);
-                if (valid[2]) *reinterpret_cast<float2 *>(o1 + f * os) = make_float2(res[2], res[3]);
+            float *w1 = w0 + ni;
+            if (full) {
+                *reinterpret_cast<float2 *>(w0) = make_float2(res[0], res[1]);
+                *reinterpret_cast<float2 *>(w1) = make_float2(res[2], res[3]);
             } else {
-                if (valid[0]) o0[f * os] = res[0];
-                if (valid[1]) o0[f * os + 1] = res[1];
-                if (valid[2]) o1[f * os] = res[2];
-                if (valid[3]) o1[f * os + 1] = res[3];
+                if (valid[0]) w0[0] = res[0];
+                if (valid[1]) w0[1] = res[1];
+                if (valid[2]) w1[0] = res[2];
+                if (valid[3]) w1[1] = res[3];
             }
         }
+        w0 += os;
     }
 }
 
 template <int DEG>
-__global__ void __launch_bounds__(TT * TT) k_interp_tiled(const __grid_constant__ InterpArgs a) {
+__global__ void __launch_bounds__(NTHR_TILED, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int by = remap_tile_row(blockIdx.y, gridDim.y);
     const int tile = by * gridDim.x + blockIdx.x;
     const TileDesc td = a.tiles[tile];
     if (td.nfast == 0) return;
+    for (int k = threadIdx.x; k < NSTAGE * TILE_CAP; k += NTHR_TILED) smem[k] = 0.f;
+    __syncthreads();
+    if (threadIdx.x >= TT * TT) {
+        if (td.panel) producer_warp(a, a.zin + a.panel_stride, td, a.src2.ni, a.src2.j2 - a.src2.j1 + 1, smem);
+        else producer_warp(a, a.zin, td, a.src.ni, a.src.j2 - a.src.j1 + 1, smem);
+        return;
+    }
     const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
     const Quad q = quad_of_thread(blockIdx.x, by);
-    if (td.panel) tiled_body<DEG>(a.src2, a, a.zin + a.panel_stride, td, q, fast, smem);
-    else tiled_body<DEG>(a.src, a, a.zin, td, q, fast, smem);
+    if (td.panel) compute_warps<DEG>(a.src2, a, td, q, fast, smem);
+    else compute_warps<DEG>(a.src, a, td, q, fast, smem);
 }
 
 }  // namespace
