@@ -112,6 +112,10 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 tiled, 4 per-point on the compacted list
     int last_nlist = 0;
     DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4];
+    // host-pointer pipeline (ezsint_pipelined): two copy streams beside the compute stream, double-buffered chunks
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    DevBuf pipe_in[2], pipe_out[2];
 };
 thread_local Session S;
 
@@ -864,6 +868,54 @@ bool session_ok(const char *who) {
     return true;
 }
 
+int ensure_pipe() {
+    if (S.s_h2d) return 0;
+    CUDA_OK(cudaStreamCreateWithFlags(&S.s_h2d, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&S.s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CUDA_OK(cudaEventCreateWithFlags(&S.ev_in[k], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&S.ev_comp[k], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&S.ev_out[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// Host arrays in, host arrays out, several fields: the fields are cut into chunks of levels and the three legs
+// (host->device copy, interpolation, device->host copy) run on three streams, so that the PCIe link carries
+// inputs of chunk k+1 and outputs of chunk k-1 (full duplex) while chunk k is being interpolated.
+int ezsint_pipelined(Grid &out, Grid &in, float *zout, const float *zin, int nfields, size_t nin, size_t nout) {
+    if (ensure_pipe() < 0) return -1;
+    const int chunk = nfields >= 16 ? 4 : (nfields >= 4 ? 2 : 1);
+    float *d_in[2], *d_out[2];
+    for (int k = 0; k < 2; k++) {
+        d_in[k] = (float *)S.pipe_in[k].get(nin * chunk * sizeof(float));
+        d_out[k] = (float *)S.pipe_out[k].get(nout * chunk * sizeof(float));
+        if (!d_in[k] || !d_out[k]) { fprintf(stderr, "<ezb200> cannot allocate device staging for the host-pointer pipeline\n"); return -1; }
+    }
+    // the copy streams must not run ahead of work already queued on the caller's stream
+    CUDA_OK(cudaEventRecord(S.ev_comp[0], S.stream));
+    CUDA_OK(cudaStreamWaitEvent(S.s_h2d, S.ev_comp[0], 0));
+    int rc = 0, c = 0;
+    for (int f0 = 0; f0 < nfields; f0 += chunk, c++) {
+        const int nf = (nfields - f0 < chunk) ? (nfields - f0) : chunk, b = c & 1;
+        if (c >= 2) CUDA_OK(cudaStreamWaitEvent(S.s_h2d, S.ev_comp[b], 0));      // the kernel that read this input buffer is done
+        CUDA_OK(cudaMemcpyAsync(d_in[b], zin + (size_t)f0 * nin, nin * nf * sizeof(float), cudaMemcpyHostToDevice, S.s_h2d));
+        CUDA_OK(cudaEventRecord(S.ev_in[b], S.s_h2d));
+        CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_in[b], 0));
+        if (c >= 2) CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_out[b], 0));      // the copy that drained this output buffer is done
+        int r = sint_any_dev(out, in, d_out[b], d_in[b], nf, (long)nin, (long)nout, 0, 1);
+        if (r < 0) { cudaStreamSynchronize(S.s_h2d); cudaStreamSynchronize(S.stream); cudaStreamSynchronize(S.s_d2h); return r; }
+        if (r > rc) rc = r;
+        CUDA_OK(cudaEventRecord(S.ev_comp[b], S.stream));
+        CUDA_OK(cudaStreamWaitEvent(S.s_d2h, S.ev_comp[b], 0));
+        CUDA_OK(cudaMemcpyAsync(zout + (size_t)f0 * nout, d_out[b], nout * nf * sizeof(float), cudaMemcpyDeviceToHost, S.s_d2h));
+        CUDA_OK(cudaEventRecord(S.ev_out[b], S.s_d2h));
+    }
+    CUDA_OK(cudaStreamSynchronize(S.s_d2h));
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    return rc;
+}
+
 int ezsint_n(float *zout, float *zin, int nfields) {
     std::lock_guard<std::recursive_mutex> lk(g_mtx);
     if (!session_ok("c_ezsint")) return -1;
@@ -875,6 +927,7 @@ int ezsint_n(float *zout, float *zin, int nfields) {
         CUDA_OK(cudaStreamSynchronize(S.stream));
         return 1;
     }
+    if (nfields >= 2 && !is_device_ptr(zin) && !is_device_ptr(zout)) return ezsint_pipelined(out, in, zout, zin, nfields, nin, nout);
     Staged si, so;
     if (stage_in(si, S.st_in[0], zin, nin * nfields) < 0) return -1;
     if (stage_out(so, S.st_out[0], zout, nout * nfields) < 0) return -1;
