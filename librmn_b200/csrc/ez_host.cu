@@ -48,7 +48,7 @@ struct TilePlan {   // classification of the target points for the tiled kernel 
     TileDesc *d_tiles = nullptr;
     uint32_t *d_flags = nullptr;
     int *d_list = nullptr;
-    int nlist = 0, ntiles_fast = 0;
+    int nlist = 0, ntiles_fast = 0, cap = 0;
 };
 
 struct Gset {   // _gridset, ez_def.h:148-166, device-resident
@@ -651,6 +651,7 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     }
     tp.nlist = (int)hc[0];
     tp.ntiles_fast = (int)hc[1];
+    tp.cap = ((int)hc[2] + 3) & ~3;   // floats per staged level: the largest tile box, 16-byte granular
     // the tile kernel pays off when most points take it (target as fine as the source); otherwise keep the per-point kernel
     tp.suitable = tp.ntiles_fast > 0 && (size_t)tp.nlist * 2 <= (size_t)a.npts;
     if (tp.suitable && tp.nlist > 0) {
@@ -795,6 +796,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
         if (tp->suitable) {
             a.tiles = tp->d_tiles;
             a.tile_flags = tp->d_flags;
+            a.tile_cap = tp->cap;
             a.list = tp->d_list;
             a.nlist = tp->nlist;
         }

@@ -495,28 +495,51 @@ __global__ void __launch_bounds__(TPB) k_minmax(InterpArgs a, unsigned int *scra
     }
 }
 
-// ez_calcpoleval.inc:30-45: strictly sequential fp32 accumulation (one thread per field and pole) so the
-// pole value is bit-identical to the reference's; plus the DEHORS fudge value of ez_corrval.c:62-91.
-__global__ void k_field_scalars(InterpArgs a, int need_poles, int need_minmax, FieldScalars *fs, const unsigned int *scratch) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int f = t >> 1, which = t & 1;
+// ez_calcpoleval.inc:30-45: strictly sequential fp32 accumulation, so the pole value is bit-identical to the
+// reference's; plus the DEHORS fudge value of ez_corrval.c:62-91.  One CTA per (field, pole): the row (and, for
+// Z/E sources, its products with the axis spacing -- each an independent, identically rounded operation) is
+// fetched by the whole CTA into shared memory in chunks, then ONE thread adds the chunk in index order.
+constexpr int FS_CHUNK = 2048;
+__global__ void __launch_bounds__(256) k_field_scalars(InterpArgs a, int need_poles, int need_minmax, FieldScalars *fs, const unsigned int *scratch) {
+    __shared__ float s_row[FS_CHUNK];
+    __shared__ float s_acc;
+    const int f = blockIdx.x >> 1, which = blockIdx.x & 1;
     if (f >= a.nfields) return;
     const GridDev &g = a.src;
     if (need_poles) {
         FieldFetch ff = make_fetch(g, a.zin + (long)f * a.in_stride, a.o.sym_sign);
-        int jrow = which ? g.j1 : g.j2;   // north pole uses the last row, south the first (ez_corrval.c:133-140)
-        float p = 0.0f;
-        if (g.grtyp == 'Z' && g.grref == 'E') {
-            for (int i = 1; i <= g.ni - 1; i++) p = p + ff(i, jrow) * (__ldg(g.ax + i) - __ldg(g.ax + i - 1));
-            float span = __ldg(g.ax + g.ni - 1) - __ldg(g.ax);
-            if (span != 0.0f) p = p / span;
-        } else {
-            for (int i = 1; i <= g.ni; i++) p = p + ff(i, jrow);
-            p = p / (1.0f * (float)g.ni);
+        const int jrow = which ? g.j1 : g.j2;   // north pole uses the last row, south the first (ez_corrval.c:133-140)
+        const bool weighted = (g.grtyp == 'Z' && g.grref == 'E');
+        const int n = weighted ? g.ni - 1 : g.ni;
+        if (threadIdx.x == 0) s_acc = 0.0f;
+        for (int i0 = 0; i0 < n; i0 += FS_CHUNK) {
+            const int m = min(FS_CHUNK, n - i0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < m; k += blockDim.x) {
+                const int i = i0 + k + 1;
+                float v = ff(i, jrow);
+                if (weighted) v = v * (__ldg(g.ax + i) - __ldg(g.ax + i - 1));
+                s_row[k] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float p = s_acc;
+                for (int k = 0; k < m; k++) p = p + s_row[k];
+                s_acc = p;
+            }
         }
-        if (which) fs[f].pole_s = p; else fs[f].pole_n = p;
+        if (threadIdx.x == 0) {
+            float p = s_acc;
+            if (weighted) {
+                float span = __ldg(g.ax + g.ni - 1) - __ldg(g.ax);
+                if (span != 0.0f) p = p / span;
+            } else {
+                p = p / (1.0f * (float)g.ni);
+            }
+            if (which) fs[f].pole_s = p; else fs[f].pole_n = p;
+        }
     }
-    if (which == 0) {
+    if (which == 0 && threadIdx.x == 0) {
         float fudge = 0.0f;
         if (need_minmax) {
             float valmin = ord2f(scratch[2 * f]), valmax = ord2f(scratch[2 * f + 1]);
@@ -588,8 +611,7 @@ void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldSc
         dim3 grid(bx, a.nfields);
         k_minmax<<<grid, TPB, 0, s>>>(a, scratch);
     }
-    int nt = 2 * a.nfields;
-    k_field_scalars<<<(nt + 63) / 64, 64, 0, s>>>(a, need_poles, need_minmax, fs, scratch);
+    k_field_scalars<<<2 * a.nfields, 256, 0, s>>>(a, need_poles, need_minmax, fs, scratch);
 }
 
 bool tiled_eligible(const InterpArgs &a) {
@@ -627,11 +649,12 @@ int interp(const InterpArgs &a, cudaStream_t s) {
         int ntx, nty, launches = 1;
         tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
         dim3 grid(ntx, nty);
-        const size_t smem = NSTAGE * TILE_CAP * sizeof(float);
+        const size_t smem = (size_t)NSTAGE * LPS * a.tile_cap * sizeof(float);
         static bool attr_set = false;
-        if (!attr_set && smem > 48 * 1024) {
-            cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (!attr_set) {
+            const int mx = NSTAGE * LPS * TILE_CAP * (int)sizeof(float);
+            cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             attr_set = true;
         }
         if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);

@@ -251,12 +251,17 @@ __device__ __forceinline__ float eval_linear_f32(const PlanLinF &p, const float 
 // 5 linear (fp32 difference form).  Requires plain field access (no hemispheric mirror, no y inversion).
 // The grid descriptor is taken by reference straight from kernel-parameter (constant-bank) space: the Yin/Yang
 // choice is a branch around two instantiations rather than a pointer select, which would force a local copy.
+constexpr int LIST_LCH = 8;   // levels per thread when the kernel runs on the compacted list (blockIdx.y picks the chunk)
+
 template <int DEG>
 __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ z, int n, float px, float py,
                                            uint8_t zbits) {
-    float *zo = a.zout + n;
-    const int nf = a.nfields;
     const long is = a.in_stride, os = a.out_stride;
+    // the compacted list is short and its points are expensive (zone points): levels are split over blockIdx.y
+    const int f0 = a.list ? blockIdx.y * LIST_LCH : 0;
+    const int nf = a.list ? min(LIST_LCH, a.nfields - f0) : a.nfields;
+    float *zo = a.zout + n + f0 * os;
+    z += f0 * is;
     if (zbits == 0) {
         if (DEG == 0) {
             const int o = plan_nearest(g, px, py);
@@ -286,7 +291,7 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
         FieldFetch ff = make_fetch(g, z + f * is, a.o.sym_sign);
         float v = 0.f;
         if (!(zbits & (ZB_POLE_NORD | ZB_POLE_SUD)) || a.o.vector) v = interp_point(ff, g, a.o.degree, px, py);
-        zo[f * os] = zone_point(ff, g, a.o, zbits, a.fs, f, px, py, v);
+        zo[f * os] = zone_point(ff, g, a.o, zbits, a.fs, f0 + f, px, py, v);
     }
 }
 
@@ -308,8 +313,9 @@ __global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ Int
 bool launch_fast(const InterpArgs &a, cudaStream_t s) {
     if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
     if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
-    const int nb = ((a.list ? a.nlist : a.npts) + TPB - 1) / TPB;
-    if (nb <= 0) return true;
+    const int nbx = ((a.list ? a.nlist : a.npts) + TPB - 1) / TPB;
+    if (nbx <= 0) return true;
+    const dim3 nb(nbx, a.list ? (a.nfields + LIST_LCH - 1) / LIST_LCH : 1);
     switch (a.o.degree) {
         case EZ_NEAREST: k_interp_fast<0><<<nb, TPB, 0, s>>>(a); return true;
         case EZ_LINEAR:

@@ -27,12 +27,16 @@ constexpr int TO = 2 * TT;         // target points per tile side
 #define EZ_TILE_CAP 2560
 #endif
 #ifndef EZ_NSTAGE
-#define EZ_NSTAGE 4
+#define EZ_NSTAGE 3
+#endif
+#ifndef EZ_LPS
+#define EZ_LPS 4
 #endif
 #ifndef EZ_TILED_MINB
 #define EZ_TILED_MINB 3
 #endif
 constexpr int TILE_CAP = EZ_TILE_CAP;     // floats per shared-memory buffer
+constexpr int LPS = EZ_LPS;               // source levels per pipeline stage (one CTA barrier per stage)
 constexpr int NSTAGE = EZ_NSTAGE;          // buffers per CTA: the producer warp runs NSTAGE-1 source levels ahead of the compute warps
 
 template <int DEG> struct Sten {
@@ -126,7 +130,8 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     else classify_thread<DEG>(a.src, a, q, 0, fast, wc0, wr0);
     if (fast) {
         atomicMin(&s_box[0], wc0); atomicMin(&s_box[1], wr0);
-        atomicMax(&s_box[2], wc0 + Sten<DEG>::W - 1); atomicMax(&s_box[3], wr0 + Sten<DEG>::W - 1);
+        atomicMax(&s_box[2], wc0 + Sten<DEG>::W - 1);
+        atomicMax(&s_box[3], wr0 + Sten<DEG>::W - 1);
     }
     __syncthreads();
     const int c0 = s_box[0], r0 = s_box[1], c1 = s_box[2], r1 = s_box[3];
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
         td.panel = tile_panel; td.nfast = s_cnt[1]; td.nslow = s_cnt[0]; td.pad = 0;
         tiles[tile] = td;
         atomicAdd(counters + 0, (unsigned int)s_cnt[0]);
+        if (box_ok && s_cnt[1] > 0) atomicMax(counters + 2, (unsigned int)((w | 1) * h));
         if (s_cnt[1] > 0) atomicAdd(counters + 1, 1u);
     }
 }
@@ -184,15 +190,19 @@ __global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ I
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
 // CTA-wide barrier shared by the producer warp and the compute warps (they reach it from different code paths)
-constexpr int NTHR_TILED = TT * TT + 32;
+#ifndef EZ_NPROD
+#define EZ_NPROD 1
+#endif
+constexpr int NPROD = EZ_NPROD;           // producer warps per CTA (each has its own limit of outstanding cp.async requests)
+constexpr int NTHR_TILED = TT * TT + 32 * NPROD;
 __device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR_TILED) : "memory"); }
 
 // The producer warp: stages the tile's box of every source level into shared memory with cp.async (LDGSTS), one
 // level ahead of the compute warps.  Lane l copies box columns l and l+32 (boxes are at most 64 wide) of every box
 // row; per row that is two predicated 4-byte copies and two pointer bumps.  Box cells that overhang the field (a
 // window may stick out by one zero-weight row/column on the high side) are never written and keep the zero fill.
-__device__ __forceinline__ void stage_level(float *__restrict__ dst, const float *__restrict__ src, int nrow, int src_ni, int pitch, bool c0ok,
-                                            bool c1ok) {
+__device__ __forceinline__ void stage_rows(float *__restrict__ dst, const float *__restrict__ src, int nrow, int src_ni, int pitch, bool c0ok,
+                                           bool c1ok) {
 #pragma unroll 4
     for (int r = 0; r < nrow; r++) {
         if (c0ok) __pipeline_memcpy_async(dst, src, 4);
@@ -200,46 +210,62 @@ __device__ __forceinline__ void stage_level(float *__restrict__ dst, const float
         src += src_ni;
         dst += pitch;
     }
-    __pipeline_commit();
 }
 
 __device__ __forceinline__ void producer_warp(const InterpArgs &a, const float *__restrict__ zin, const TileDesc &td, int src_ni, int src_rows,
                                               float *__restrict__ smem) {
     const int lane = threadIdx.x & 31;
     const int pitch = td.w | 1;
-    const int nrow = min(td.h, src_rows - td.r0);
+    const int pw = (threadIdx.x - TT * TT) >> 5;                    // this producer warp copies box rows pw, pw + NPROD, ...
+    const int nrow = (min(td.h, src_rows - td.r0) - pw + NPROD - 1) / NPROD;
     const bool c0ok = lane < td.w && (td.c0 + lane) < src_ni;
     const bool c1ok = (lane + 32) < td.w && (td.c0 + lane + 32) < src_ni;
-    const float *src = zin + (long)td.r0 * src_ni + td.c0 + lane;
+    const float *src = zin + (long)(td.r0 + pw) * src_ni + td.c0 + lane;
     const int nf = a.nfields;
     const long is = a.in_stride;
-    // prologue: levels 0 .. NSTAGE-2 in flight (empty commit groups keep the group count uniform when nf is small)
+    // A stage holds LPS consecutive levels; the producer runs NSTAGE-1 stages ahead.  Empty commit groups keep the
+    // group count uniform at the tail.
+    const int cap = a.tile_cap;
+    const int nstages = (nf + LPS - 1) / LPS;
+    auto stage = [&](int st) {
+        if (st < nstages) {
+            float *dst = smem + (st % NSTAGE) * LPS * cap + pw * pitch + lane;
+#pragma unroll 1
+            for (int l = 0; l < LPS; l++) {
+                const int f = st * LPS + l;
+                if (f < nf) stage_rows(dst + l * cap, src + f * is, nrow, NPROD * src_ni, NPROD * pitch, c0ok, c1ok);
+            }
+        }
+        __pipeline_commit();
+    };
 #pragma unroll
-    for (int k = 0; k < NSTAGE - 1; k++) {
-        if (k < nf) stage_level(smem + k * TILE_CAP + lane, src + k * is, nrow, src_ni, pitch, c0ok, c1ok);
-        else __pipeline_commit();
-    }
-    for (int f = 0; f < nf; f++) {
-        __pipeline_wait_prior(NSTAGE - 2);   // level f has landed
-        tile_barrier();                      // ... and every compute warp is done with level f-1, whose buffer is refilled next
-        const int nxt = f + NSTAGE - 1;
-        if (nxt < nf) stage_level(smem + (nxt % NSTAGE) * TILE_CAP + lane, src + nxt * is, nrow, src_ni, pitch, c0ok, c1ok);
-        else __pipeline_commit();
+    for (int k = 0; k < NSTAGE - 1; k++) stage(k);
+    for (int st = 0; st < nstages; st++) {
+        __pipeline_wait_prior(NSTAGE - 2);   // stage st has landed
+        tile_barrier();                      // ... and every compute warp is done with stage st-1, whose buffers are refilled next
+        stage(st + NSTAGE - 1);
     }
 }
 
+// The compute warps.  Arithmetic of one level for one thread (2 x 2 target points p0 p1 / p2 p3, W x W window):
+//   d_rc = z_rc - zc                                  (zc = window centre; fp32 difference form)
+//   out_p = zc (1 + s_p) + sum_r wy_p[r] * ( sum_c wx_p[c] * d_rc )
+// evaluated with packed fp32x2 instructions (FFMA2/FMUL2: sm_100 issues two fp32 FMAs per instruction, measured
+// 114 vs 72 FMA/clk/SM for scalar FFMA, scripts/ubench/ffma2.cu): the two points of a row pair share the data
+// operand (d, d) and carry their own weights in the two halves.  The window is streamed row by row, so only one
+// row of data is live in registers.
 template <int DEG>
 __device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs &a, const TileDesc &td, const Quad &q, bool fast,
                                               const float *__restrict__ smem) {
     constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
     const int ni = a.out_ni, nj = a.out_nj;
     const int pitch = td.w | 1;
-    float wx[4][W], wy[4][W], sm1[4];
+    float2 wxp[2][W], wyp[2][W], smp[2];   // [pair][k] = (weight of point 2*pair, weight of point 2*pair+1)
     bool valid[4] = {false, false, false, false};
     int base = 0;
     if (fast) {
         int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
-        float tx[4][4], ty[4][4];
+        float tx[4][4], ty[4][4], sm1[4];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
             valid[p] = q.valid(p, ni, nj);
@@ -250,6 +276,7 @@ __device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs
                 wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
             }
         }
+        float wx[4][W], wy[4][W];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
             const bool sx = valid[p] && (c0[p] != wc0), sy = valid[p] && (r0[p] != wr0);   // offset 0 or 1 inside the window
@@ -261,6 +288,15 @@ __device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs
                 wy[p][k] = valid[p] ? (sy ? hi2 : lo2) : 0.f;
             }
         }
+#pragma unroll
+        for (int pp = 0; pp < 2; pp++) {
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                wxp[pp][k] = make_float2(wx[2 * pp][k], wx[2 * pp + 1][k]);
+                wyp[pp][k] = make_float2(wy[2 * pp][k], wy[2 * pp + 1][k]);
+            }
+            smp[pp] = make_float2(sm1[2 * pp], sm1[2 * pp + 1]);
+        }
         base = (wr0 - td.r0) * pitch + (wc0 - td.c0);
     }
     const int nf = a.nfields;
@@ -268,45 +304,50 @@ __device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs
     // float2 stores need all four points and 8-byte alignment (even target row length; q.ox is even)
     const bool full = fast && ((ni & 1) == 0) && valid[3] && ((reinterpret_cast<uintptr_t>(a.zout) & 7) == 0) && ((os & 1) == 0);
     float *w0 = a.zout + (long)q.oy * ni + q.ox;
-    for (int f = 0; f < nf; f++) {
+    const int cap = a.tile_cap;
+    const int nstages = (nf + LPS - 1) / LPS;
+    for (int st = 0; st < nstages; st++) {
         tile_barrier();
+        const float *sbase = smem + (st % NSTAGE) * LPS * cap + base;
+        const int nl = min(LPS, nf - st * LPS);
         if (fast) {
-            const float *s = smem + (f % NSTAGE) * TILE_CAP + base;
-            float d[W][W];
-#pragma unroll
-            for (int r = 0; r < W; r++)
-#pragma unroll
-                for (int c = 0; c < W; c++) d[r][c] = s[r * pitch + c];
-            const float zc = d[W / 2][W / 2];
-#pragma unroll
-            for (int r = 0; r < W; r++)
-#pragma unroll
-                for (int c = 0; c < W; c++) d[r][c] = d[r][c] - zc;
-            float res[4];
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                float acc = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < nl; l++) {
+                const float *s = sbase + l * cap;
+                const float zc = s[(W / 2) * pitch + W / 2];
+                const float2 zc2 = make_float2(zc, zc);
+                float2 acc[2];
 #pragma unroll
                 for (int r = 0; r < W; r++) {
-                    float rs = wx[p][0] * d[r][0];
+                    float2 d[W];
 #pragma unroll
-                    for (int c = 1; c < W; c++) rs = fmaf(wx[p][c], d[r][c], rs);
-                    acc = fmaf(wy[p][r], rs, acc);
+                    for (int c = 0; c < W; c++) {
+                        const float v = s[r * pitch + c] - zc;
+                        d[c] = make_float2(v, v);
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        float2 rs = __fmul2_rn(wxp[pp][0], d[0]);
+#pragma unroll
+                        for (int c = 1; c < W; c++) rs = __ffma2_rn(wxp[pp][c], d[c], rs);
+                        acc[pp] = (r == 0) ? __fmul2_rn(wyp[pp][0], rs) : __ffma2_rn(wyp[pp][r], rs, acc[pp]);
+                    }
                 }
-                res[p] = zc + fmaf(zc, sm1[p], acc);
-            }
-            float *w1 = w0 + ni;
-            if (full) {
-                *reinterpret_cast<float2 *>(w0) = make_float2(res[0], res[1]);
-                *reinterpret_cast<float2 *>(w1) = make_float2(res[2], res[3]);
-            } else {
-                if (valid[0]) w0[0] = res[0];
-                if (valid[1]) w0[1] = res[1];
-                if (valid[2]) w1[0] = res[2];
-                if (valid[3]) w1[1] = res[3];
+                const float2 r01 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[0], acc[0]));
+                const float2 r23 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[1], acc[1]));
+                float *w1 = w0 + ni;
+                if (full) {
+                    *reinterpret_cast<float2 *>(w0) = r01;
+                    *reinterpret_cast<float2 *>(w1) = r23;
+                } else {
+                    if (valid[0]) w0[0] = r01.x;
+                    if (valid[1]) w0[1] = r01.y;
+                    if (valid[2]) w1[0] = r23.x;
+                    if (valid[3]) w1[1] = r23.y;
+                }
+                w0 += os;
             }
         }
-        w0 += os;
     }
 }
 
@@ -317,7 +358,7 @@ __global__ void __launch_bounds__(NTHR_TILED, EZ_TILED_MINB) k_interp_tiled(cons
     const int tile = by * gridDim.x + blockIdx.x;
     const TileDesc td = a.tiles[tile];
     if (td.nfast == 0) return;
-    for (int k = threadIdx.x; k < NSTAGE * TILE_CAP; k += NTHR_TILED) smem[k] = 0.f;
+    for (int k = threadIdx.x; k < NSTAGE * LPS * a.tile_cap; k += NTHR_TILED) smem[k] = 0.f;
     __syncthreads();
     if (threadIdx.x >= TT * TT) {
         if (td.panel) producer_warp(a, a.zin + a.panel_stride, td, a.src2.ni, a.src2.j2 - a.src2.j1 + 1, smem);

@@ -25,6 +25,7 @@ struct InterpArgs {
     int out_ni, out_nj;
     const TileDesc *tiles;
     const uint32_t *tile_flags;   // 8 words per tile: bit t = thread t takes the tile path
+    int tile_cap;                 // floats reserved per staged source level (>= the largest tile box)
     // per-point kernel restricted to a compacted list of target points (nullptr = all npts points)
     const int *list;
     int nlist;
