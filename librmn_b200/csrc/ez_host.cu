@@ -116,6 +116,7 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     DevBuf pipe_in[2], pipe_out[2];
+    DevBuf prow[2];             // synthetic pole rows of (u, v) for the polar vector correction (K18)
 };
 thread_local Session S;
 
@@ -741,7 +742,8 @@ int check_degree() {
 }
 
 // zin/zout are DEVICE pointers here.  Returns 0, 2 (extrapolated) or -1.
-int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign) {
+int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign,
+             const float *polerow = nullptr) {
     if (check_degree() < 0) return -1;
     Gset *gs = ensure_gset(out, in);
     if (!gs) return -1;
@@ -754,6 +756,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     a.nfields = nfields;
     a.npts = out.ni * out.nj;
     a.o = snapshot_opts(vector, sym_sign);
+    a.polerow = polerow;
     int rc = 0;
     if (gs->yy) {
         Grid *yin = grid_of(in.subgrid[0]), *yan = grid_of(in.subgrid[1]);
@@ -997,17 +1000,46 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
         }
         r1 = r2 = 1;
     } else {
-        r1 = sint_dev(out, *eff_in, d_uo, ui, nfields, in_stride, out_stride, 1, +1);
-        r2 = sint_dev(out, *eff_in, d_vo, vi, nfields, in_stride, out_stride, 1, -1);
-        if (r1 < 0 || r2 < 0) return -1;
+        // ez_corrvec (ezuvint.c:77-79): points next to a pole are re-interpolated from strips whose pole row is synthetic
+        const float *prow_u = nullptr, *prow_v = nullptr;
         if (eff_in->nsubgrids == 0 && S.opt.polar_correction == 1) {
             Gset *gs = ensure_gset(out, *eff_in);
-            if (gs && (gs->counts[1] + gs->counts[2] + gs->counts[3] + gs->counts[4]) > 0 && !g_warned_polarwind) {
-                g_warned_polarwind = true;
-                fprintf(stderr, "<ezb200> warning: polar wind correction (ez_corrvec, K18) is not implemented yet; "
-                                "vector values in the two source rows next to a pole are plain interpolants\n");
+            if (!gs) return -1;
+            if ((gs->counts[1] + gs->counts[2] + gs->counts[3] + gs->counts[4]) > 0) {
+                if (eff_in->needs_expansion || eff_in->axe_y_inverse) {
+                    if (!g_warned_polarwind) {
+                        g_warned_polarwind = true;
+                        fprintf(stderr, "<ezb200> warning: polar wind correction is not applied to hemispheric / y-inverted sources; "
+                                        "vector values in the two source rows next to a pole are plain interpolants\n");
+                    }
+                } else {
+                    const size_t nrow = (size_t)nfields * 2 * eff_in->ni;
+                    float *pu = (float *)S.prow[0].get(nrow * sizeof(float)), *pv = (float *)S.prow[1].get(nrow * sizeof(float));
+                    if (!pu || !pv) return -1;
+                    PolarWindArgs pw;
+                    memset(&pw, 0, sizeof(pw));
+                    pw.src = to_dev(*eff_in);
+                    pw.u = ui; pw.v = vi;
+                    pw.stride = in_stride;
+                    pw.nfields = nfields;
+                    // auxiliary polar-stereographic grids: cxgaig(pi 0, pj 0, d60 1000, dgrw 0) then the decode c_ezqkdef performs
+                    for (int h = 0; h < 2; h++) {
+                        float xg[4] = {0.0f, 0.0f, 1000.0f, 0.0f};
+                        int ig[4];
+                        ezh::cxgaig(h ? 'S' : 'N', ig, xg);
+                        ezh::cigaxg(h ? 'S' : 'N', xg, ig);
+                        (h ? pw.dgrw_s : pw.dgrw_n) = xg[3];
+                    }
+                    pw.prow_u = pu; pw.prow_v = pv;
+                    ezk::polar_wind_rows(pw, S.stream);
+                    S.launches++;
+                    prow_u = pu; prow_v = pv;
+                }
             }
         }
+        r1 = sint_dev(out, *eff_in, d_uo, ui, nfields, in_stride, out_stride, 1, +1, prow_u);
+        r2 = sint_dev(out, *eff_in, d_vo, vi, nfields, in_stride, out_stride, 1, -1, prow_v);
+        if (r1 < 0 || r2 < 0) return -1;
     }
     if (wind_dev(out, *eff_in, d_uo, d_vo, nfields, out_stride, mode) < 0) return -1;
     return (r1 == 2 || r2 == 2) ? 2 : 0;

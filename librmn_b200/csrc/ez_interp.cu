@@ -57,9 +57,10 @@ struct StripFetch {
     FieldFetch f;
     int jbase, pole_row, jsrc0;
     float poleval;
+    const float *polerow;   // vectors: a synthetic pole ROW (ez_calcnpolarwind / ez_calcspolarwind) instead of one pole value
     __device__ __forceinline__ float operator()(int i, int j) const {
         int r = j - jbase;
-        if (r == pole_row) return poleval;
+        if (r == pole_row) return polerow ? __ldg(polerow + i - 1) : poleval;
         return f(i, jsrc0 + (pole_row == 0 ? r - 1 : r));
     }
 };
@@ -363,10 +364,13 @@ __device__ __forceinline__ FieldFetch make_fetch(const GridDev &g, const float *
 }
 
 // ez_corrval_aunord.c:39-112 / ez_corrval_ausud.c:46-129 for one point
-__device__ __noinline__ float polar_point(const FieldFetch &ff, const GridDev &g, int degree, bool north, float poleval, float px, float py) {
+// (scalars: poleval ; vectors, ez_corrvec_aunord.c:39-133 / ez_corrvec_ausud.c: the same strips with a pole row)
+__device__ __noinline__ float polar_point(const FieldFetch &ff, const GridDev &g, int degree, bool north, float poleval, const float *polerow,
+                                          float px, float py) {
     StripFetch s;
     s.f = ff;
     s.poleval = poleval;
+    s.polerow = polerow;
     const bool irr = (g.grtyp == 'Z' || g.grtyp == 'G');   // ('E' has no axes in the reference: regular strip)
     if (north) {
         int j1s = g.j2 - 2, j2s = j1s + 3;
@@ -412,7 +416,7 @@ __device__ __noinline__ float polar_point(const FieldFetch &ff, const GridDev &g
 
 // everything ez_corrval.c:54-143 does to one point carrying zone bits
 __device__ __noinline__ float zone_point(const FieldFetch &ff, const GridDev &g, const InterpOpts &o, uint8_t bits, const FieldScalars *fs,
-                                         int f, float px, float py, float normal) {
+                                         const float *prow, int f, float px, float py, float normal) {
     float v = normal;
     if (bits & ZB_DEHORS) {
         if (o.extrap >= EZ_MAXIMUM)
@@ -420,9 +424,17 @@ __device__ __noinline__ float zone_point(const FieldFetch &ff, const GridDev &g,
         else
             v = interp_point(ff, g, o.extrap, px, py);
     }
-    if (o.vector) return v;
-    if (bits & ZB_AU_NORD) v = polar_point(ff, g, o.degree, true, fs[f].pole_n, px, py);
-    if (bits & ZB_AU_SUD) v = polar_point(ff, g, o.degree, false, fs[f].pole_s, px, py);
+    if (o.vector) {
+        // ez_corrvec.c:24-48: only the AU_NORD / AU_SUD lists are rewritten, from strips whose pole row is synthetic
+        if (prow) {
+            const float *rows = prow + (long)f * 2 * g.ni;
+            if (bits & ZB_AU_NORD) v = polar_point(ff, g, o.degree, true, 0.f, rows, px, py);
+            if (bits & ZB_AU_SUD) v = polar_point(ff, g, o.degree, false, 0.f, rows + g.ni, px, py);
+        }
+        return v;
+    }
+    if (bits & ZB_AU_NORD) v = polar_point(ff, g, o.degree, true, fs[f].pole_n, nullptr, px, py);
+    if (bits & ZB_AU_SUD) v = polar_point(ff, g, o.degree, false, fs[f].pole_s, nullptr, px, py);
     if (bits & ZB_POLE_NORD) v = fs[f].pole_n;
     if (bits & ZB_POLE_SUD) v = fs[f].pole_s;
     return v;
@@ -436,7 +448,7 @@ __device__ __forceinline__ void ref_point_body(const GridDev &g, const InterpArg
     for (int f = 0; f < a.nfields; f++) {
         FieldFetch ff = make_fetch(g, zbase + (long)f * a.in_stride, a.o.sym_sign);
         float v = interp_point(ff, g, a.o.degree, px, py);
-        if (zbits) v = zone_point(ff, g, a.o, zbits, a.fs, f, px, py, v);
+        if (zbits) v = zone_point(ff, g, a.o, zbits, a.fs, a.polerow, f, px, py, v);
         a.zout[(long)f * a.out_stride + n] = v;
     }
 }

@@ -291,7 +291,7 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
         FieldFetch ff = make_fetch(g, z + f * is, a.o.sym_sign);
         float v = 0.f;
         if (!(zbits & (ZB_POLE_NORD | ZB_POLE_SUD)) || a.o.vector) v = interp_point(ff, g, a.o.degree, px, py);
-        zo[f * os] = zone_point(ff, g, a.o, zbits, a.fs, f0 + f, px, py, v);
+        zo[f * os] = zone_point(ff, g, a.o, zbits, a.fs, a.polerow, f0 + f, px, py, v);
     }
 }
 

@@ -21,6 +21,7 @@ struct InterpArgs {
     int npts;
     InterpOpts o;
     const FieldScalars *fs; // device per-field scalars (pole means, fudge) or nullptr
+    const float *polerow;   // vectors: synthetic pole rows of this component, [nfields][north, south][ni], or nullptr (K18)
     // tiled kernel (ez_interp_tiled.cuh): target grid shape, per-tile descriptors and thread masks
     int out_ni, out_nj;
     const TileDesc *tiles;
@@ -45,6 +46,16 @@ struct WindArgs {
     int mode;               // 0: uv(src frame) -> uv(dst frame) ; 1: -> (speed,direction) only ; 2: (speed,direction) -> uv(dst)
 };
 
+// K18 synthetic pole rows for vectors (ez_calcnpolarwind.c / ez_calcspolarwind.c): prow_u, prow_v are [nfields][2][ni]
+struct PolarWindArgs {
+    GridDev src;
+    const float *u, *v;     // device source components, nfields fields `stride` apart
+    long stride;
+    int nfields;
+    float dgrw_n, dgrw_s;   // dgrw of the auxiliary 'N' / 'S' grids after the cxgaig -> cigaxg round trip
+    float *prow_u, *prow_v;
+};
+
 namespace ezk {
 void calclatlon(const GridDev &g, float *lat, float *lon, int npts, cudaStream_t s);
 void calcxy(const GridDev &src, int njs, const float *lat, float *lon, int writeback_lon, float *x, float *y, uint8_t *zb,
@@ -67,6 +78,8 @@ void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask
                    int linear, cudaStream_t s);
 // K17 wind rotation
 void wind(const WindArgs &a, cudaStream_t s);
+// K18 synthetic pole rows for vectors (ez_calcnpolarwind.c / ez_calcspolarwind.c)
+void polar_wind_rows(const PolarWindArgs &a, cudaStream_t s);
 // B-grid pole-row averaging, ez_corrbgd.inc:29-52
 void corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem, cudaStream_t s);
 }  // namespace ezk

@@ -141,9 +141,140 @@ __global__ void __launch_bounds__(TPB) k_wind(WindArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K18: the synthetic pole row of a vector field, ez_calcnpolarwind.c:59-125 / ez_calcspolarwind.c.
+// One CTA per (field, pole).  The reference's sequence, per source column i of the row next to the pole:
+//   (lat, lon) of the grid point (c_gdllfxy_orig; rotated-frame coordinates for Z/E sources, :70-83)
+//   (u, v) -> (speed, direction) on an 'A' grid ; -> (u, v) on a polar-stereographic grid centred on the pole (:85-95)
+//   pole value = row mean of those (u, v) (ez_calcpoleval: sequential fp32 sum) ; -> (speed, direction) at the pole (:97-103)
+//   direction_i = direction_pole +/- lon_i, same speed ; -> (u, v) on the 'A' grid = the pole row (:106-114)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_point_lonlat(const GridDev &g, int i, int y, float &plon, float &plat) {
+    // c_gdllfxy_orig(gdin, lat, lon, x = i + 1, y), gdllfxy.c:251-386 ; then ez_gfxyfll for Z/E (ez_calcnpolarwind.c:70-83)
+    const float xf = (float)(i + 1), yf = (float)y;
+    float lon = 0.f, lat = 0.f;
+    switch (g.grtyp) {
+        case 'A': case 'B': case 'L':
+            lat = (float)(((double)yf - 1.0) * (double)g.xg[2] + (double)g.xg[0]);
+            lon = (float)(((double)xf - 1.0) * (double)g.xg[3] + (double)g.xg[1]);
+            lon = (float)fmod((double)lon + 360.0, 360.0);
+            break;
+        case 'E': {
+            const float dlat = (float)(180.0 / (double)g.nj), dlon = (float)(360.0 / (double)(g.ni - 1));
+            const float swlat = (float)(-90.0 + 0.5 * (double)dlat), swlon = 0.0f;
+            const float tx = (float)(((double)xf - 1.0) * (double)dlon + (double)swlon);
+            const float ty = (float)(((double)yf - 1.0) * (double)dlat + (double)swlat);
+            ez_rotate_ll(g.ri, tx, ty, lon, lat);
+            break;
+        }
+        case '#': case 'Z': case 'G': {
+            int indx = (int)xf - 1, indy = (int)yf - 1;
+            indx = indx < 0 ? 0 : indx;
+            indy = indy < 0 ? 0 : indy;
+            indx = indx > g.ni - 2 ? g.ni - 2 : indx;
+            indy = indy > g.j2 - 2 ? g.j2 - 2 : indy;
+            const float delxx = __ldg(g.ax + indx + 1) - __ldg(g.ax + indx);
+            const float tx = (float)((double)__ldg(g.ax + indx) + (((double)xf - 1.0 - (double)indx) * (double)delxx));
+            const float delyy = __ldg(g.ay + indy + 1) - __ldg(g.ay + indy);
+            const float ty = (float)((double)__ldg(g.ay + indy) + (((double)yf - 1.0 - (double)indy) * (double)delyy));
+            if (g.grref == 'E') {
+                ez_rotate_ll(g.ri, tx, ty, lon, lat);
+            } else if (g.grref == 'L') {
+                lat = ty * g.xgref[2] + g.xgref[0];
+                lon = tx * g.xgref[3] + g.xgref[1];
+                lon = (float)fmod((double)lon + 360.0, 360.0);
+            }
+            break;
+        }
+        default: break;
+    }
+    if (g.grtyp == 'Z' && g.grref == 'E') {
+        float lr, ar;
+        ez_rotate_ll(g.r, lon, lat, lr, ar);
+        lon = lr;
+        lat = ar;
+    }
+    plon = lon;
+    plat = lat;
+}
+
+constexpr int PW_CHUNK = 1024;
+__global__ void __launch_bounds__(256) k_polar_wind(PolarWindArgs a) {
+    __shared__ float s_u[PW_CHUNK], s_v[PW_CHUNK];
+    __shared__ float s_acc[2], s_pole[2];
+    const int f = blockIdx.x >> 1, south = blockIdx.x & 1;
+    const GridDev &g = a.src;
+    const int ni = g.ni, nj = g.j2 - g.j1 + 1;
+    const int row = south ? 1 : nj;
+    const float *u = a.u + (long)f * a.stride + (long)(row - 1) * ni;
+    const float *v = a.v + (long)f * a.stride + (long)(row - 1) * ni;
+    const char t = south ? 'S' : 'N';
+    const float dgrw = south ? a.dgrw_s : a.dgrw_n;
+    const bool weighted = (g.grtyp == 'Z' && g.grref == 'E');
+    const int n = weighted ? ni - 1 : ni;
+    if (threadIdx.x == 0) { s_acc[0] = 0.f; s_acc[1] = 0.f; }
+    for (int i0 = 0; i0 < n; i0 += PW_CHUNK) {
+        const int m = min(PW_CHUNK, n - i0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const int i = i0 + k;
+            float plon, plat;
+            src_point_lonlat(g, i, row, plon, plat);
+            float z1 = u[i], z2 = v[i];
+            llwfgdw1('A', 0.f, plon, z1, z2);       // c_gdwdfuv on the auxiliary 'A' grid
+            gdwfllw1(t, dgrw, plon, z1, z2);        // c_gduvfwd on the auxiliary polar-stereographic grid
+            if (weighted) {
+                const float dx = __ldg(g.ax + i + 1) - __ldg(g.ax + i);
+                z1 = z1 * dx;
+                z2 = z2 * dx;
+            }
+            s_u[k] = z1;
+            s_v[k] = z2;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {   // ez_calcpoleval.inc:30-45: sequential fp32 accumulation
+            const float *sv = threadIdx.x ? s_v : s_u;
+            float p = s_acc[threadIdx.x];
+            for (int k = 0; k < m; k++) p = p + sv[k];
+            s_acc[threadIdx.x] = p;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float up = s_acc[0], vp = s_acc[1];
+        if (weighted) {
+            const float span = __ldg(g.ax + ni - 1) - __ldg(g.ax);
+            if (span != 0.0f) { up = up / span; vp = vp / span; }
+        } else {
+            up = up / (1.0f * (float)ni);
+            vp = vp / (1.0f * (float)ni);
+        }
+        llwfgdw1(t, dgrw, 0.0f, up, vp);            // (speed, direction) at the pole, lon = 0
+        s_pole[0] = up;
+        s_pole[1] = vp;
+    }
+    __syncthreads();
+    const float spd0 = s_pole[0], wd0 = s_pole[1];
+    float *pu = a.prow_u + ((long)f * 2 + south) * ni, *pv = a.prow_v + ((long)f * 2 + south) * ni;
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) {
+        float plon, plat;
+        src_point_lonlat(g, i, row, plon, plat);
+        // the i = 0 entry adds the longitude for BOTH poles (ez_calcspolarwind.c:108-113 subtracts it only for i >= 1)
+        float wd = (i == 0 || !south) ? wd0 + plon : wd0 - plon;
+        float sp = spd0;
+        gdwfllw1('A', 0.f, plon, sp, wd);
+        pu[i] = sp;
+        pv[i] = wd;
+    }
+}
+
 }  // namespace
 
 namespace ezk {
+void polar_wind_rows(const PolarWindArgs &a, cudaStream_t s) {
+    if (a.nfields <= 0) return;
+    k_polar_wind<<<2 * a.nfields, 256, 0, s>>>(a);
+}
 void wind(const WindArgs &a, cudaStream_t s) {
     if (a.npts <= 0 || a.nfields <= 0) return;
     k_wind<<<(a.npts + TPB - 1) / TPB, TPB, 0, s>>>(a);

@@ -48,6 +48,27 @@ def small_cases(lib, degree):
     c.src_lon, c.src_lat = configs._ll_grid(96, 48, -88.0, 0.0, 3.75, 3.75)
     c.opts = {"interp_degree": degree}
     cs.append(c)
+    # winds from GLOBAL sources: the polar vector correction (ez_corrvec, ez_calcnpolarwind / ez_calcspolarwind)
+    c = configs.c5(lib, res_src=3.0, res_dst=2.5, degree=degree)      # Z/E global: ax-weighted pole means, rotated-frame longitudes
+    c.vector = True
+    c.name += "_winds"
+    cs.append(c)
+    c = configs.Case("L144x73_to_L_winds_%s" % degree, lib)           # regular 'L' global, wrap extension 2
+    c.gdin = configs.def_L(lib, 144, 73, -90.0, 0.0, 2.5, 2.5)
+    c.gdout = configs.def_L(lib, 100, 91, -90.0, 0.0, 2.0, 3.6)
+    c.src_shape, c.dst_shape = (73, 144), (91, 100)
+    c.src_lon, c.src_lat = configs._ll_grid(144, 73, -90.0, 0.0, 2.5, 2.5)
+    c.opts = {"interp_degree": degree}
+    c.vector = True
+    cs.append(c)
+    c = configs.Case("G96x48_to_L_winds_%s" % degree, lib)            # Gaussian source: irregular strip at both caps
+    c.gdin = lib.ezqkdef(96, 48, "G", 0, 0, 0, 0)
+    c.gdout = configs.def_L(lib, 90, 46, -90.0, 0.0, 4.0, 4.0)
+    c.src_shape, c.dst_shape = (48, 96), (46, 90)
+    c.src_lon, c.src_lat = configs._ll_grid(96, 48, -88.0, 0.0, 3.75, 3.75)
+    c.opts = {"interp_degree": degree}
+    c.vector = True
+    cs.append(c)
     return cs
 
 
