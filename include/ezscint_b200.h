@@ -87,8 +87,26 @@ int32_t c_gdll(int32_t gdid, float *lat, float *lon);                           
 int32_t gdll_(int32_t *gdid, float *lat, float *lon);
 int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int32_t n);   /* ref :138 (gdxyfll.c:190) */
 int32_t gdxyfll_(int32_t *gdid, float *x, float *y, float *lat, float *lon, int32_t *n);
-int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n); /* ref :117 (gdxysval.c:50) */
-int32_t gdxysval_(int32_t *gdin, float *zout, float *zin, float *x, float *y, int32_t *n);
+int32_t c_gdllfxy(int32_t gdid, float *lat, float *lon, float *x, float *y, int32_t n);   /* ref :102 (gdllfxy.c:30) */
+int32_t gdllfxy_(int32_t *gdid, float *lat, float *lon, float *x, float *y, int32_t *n);  /* ref :101 */
+
+/* ---- scattered-point API: the same kernels at caller-supplied points (no zone correction, as in the reference) ---- */
+int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n); /* ref :120 (gdxysval.c:50) */
+int32_t gdxysval_(int32_t *gdin, float *zout, float *zin, float *x, float *y, int32_t *n); /* ref :119 */
+int32_t c_gdllsval(int32_t gdid, float *zout, float *zin, float *lat, float *lon, int32_t n);   /* ref :108 (gdllsval.c:35) */
+int32_t gdllsval_(int32_t *gdid, float *zout, float *zin, float *lat, float *lon, int32_t *n);  /* ref :107 */
+int32_t c_gdxyvval(int32_t gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t n);      /* ref :126 (gdxyvval.c:38) */
+int32_t gdxyvval_(int32_t *gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t *n);     /* ref :125 */
+int32_t c_gdllvval(int32_t gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t n);  /* ref :111 (gdllvval.c:37) */
+int32_t gdllvval_(int32_t *gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t *n); /* ref :110 */
+int32_t c_gdxywdval(int32_t gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t n);     /* ref :123 (gdxywdval.c:38) */
+int32_t gdxywdval_(int32_t *gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t *n);    /* ref :122 */
+int32_t c_gdllwdval(int32_t gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t n); /* ref :114 (gdllwdval.c:36) */
+int32_t gdllwdval_(int32_t *gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t *n);/* ref :113 */
+int32_t c_gdwdfuv(int32_t gdid, float *uullout, float *vvllout, float *uuin, float *vvin, float *latin, float *lonin, int32_t npts);   /* ref :132 (gdwdfuv.c:100) */
+int32_t gdwdfuv_(int32_t *gdid, float *uullout, float *vvllout, float *uuin, float *vvin, float *latin, float *lonin, int32_t *npts);  /* ref :131 */
+int32_t c_gduvfwd(int32_t gdid, float *uugdout, float *vvgdout, float *uullin, float *vvllin, float *latin, float *lonin, int32_t npts);  /* ref :129 (gduvfwd.c:112) */
+int32_t gduvfwd_(int32_t *gdid, float *uugdout, float *vvgdout, float *uullin, float *vvllin, float *latin, float *lonin, int32_t *npts); /* ref :128 */
 int     c_gdsetmask(int gdid, int *mask);                                          /* ref :146 (ez_mask.c:67) */
 int     gdsetmask_(int *gdid, int *mask);
 int     c_gdgetmask(int gdid, int *mask);                                          /* ref :149 (ez_mask.c:89) */

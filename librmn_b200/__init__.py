@@ -71,6 +71,12 @@ class EzLib:
         L.c_gdll.argtypes = [_i32, _f32p, _f32p]
         L.c_gdxyfll.argtypes = [_i32, _f32p, _f32p, _f32p, _f32p, _i32]
         L.c_gdxysval.argtypes = [_i32, _f32p, _f32p, _f32p, _f32p, _i32]
+        for nm in ('c_gdllfxy', 'c_gdllsval'):
+            if hasattr(L, nm):
+                getattr(L, nm).argtypes = [_i32, _f32p, _f32p, _f32p, _f32p, _i32]
+        for nm in ('c_gdxyvval', 'c_gdllvval', 'c_gdxywdval', 'c_gdllwdval', 'c_gdwdfuv', 'c_gduvfwd'):
+            if hasattr(L, nm):
+                getattr(L, nm).argtypes = [_i32] + [_f32p] * 6 + [_i32]
         L.c_ezgprm.argtypes = [_i32, C.c_char_p] + [C.POINTER(_i32)] * 6
         L.c_ezgxprm.argtypes = [_i32, C.POINTER(_i32), C.POINTER(_i32), C.c_char_p] + [C.POINTER(_i32)] * 4 + [C.c_char_p] + [C.POINTER(_i32)] * 4
         L.c_ezget_nsubgrids.argtypes = [_i32]
@@ -158,6 +164,40 @@ class EzLib:
     def gdxysval(self, gdin, zout, zin, x, y):
         _check_f32(zout, zin, x, y)
         return self.lib.c_gdxysval(gdin, _ptr(zout), _ptr(zin), _ptr(x), _ptr(y), int(x.size if isinstance(x, np.ndarray) else x.numel()))
+
+    @staticmethod
+    def _n(a):
+        return int(a.size if isinstance(a, np.ndarray) else a.numel())
+
+    def gdllfxy(self, gdid, lat, lon, x, y):
+        _check_f32(lat, lon, x, y)
+        return self.lib.c_gdllfxy(gdid, _ptr(lat), _ptr(lon), _ptr(x), _ptr(y), self._n(x))
+
+    def gdllsval(self, gdid, zout, zin, lat, lon):
+        _check_f32(zout, zin, lat, lon)
+        return self.lib.c_gdllsval(gdid, _ptr(zout), _ptr(zin), _ptr(lat), _ptr(lon), self._n(lat))
+
+    def _pts6(self, fn, gdid, a, b, c, d, e, f):
+        _check_f32(a, b, c, d, e, f)
+        return fn(gdid, _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(e), _ptr(f), self._n(e))
+
+    def gdxyvval(self, gdin, uuout, vvout, uuin, vvin, x, y):
+        return self._pts6(self.lib.c_gdxyvval, gdin, uuout, vvout, uuin, vvin, x, y)
+
+    def gdllvval(self, gdid, uuout, vvout, uuin, vvin, lat, lon):
+        return self._pts6(self.lib.c_gdllvval, gdid, uuout, vvout, uuin, vvin, lat, lon)
+
+    def gdxywdval(self, gdin, uuout, vvout, uuin, vvin, x, y):
+        return self._pts6(self.lib.c_gdxywdval, gdin, uuout, vvout, uuin, vvin, x, y)
+
+    def gdllwdval(self, gdid, uuout, vvout, uuin, vvin, lat, lon):
+        return self._pts6(self.lib.c_gdllwdval, gdid, uuout, vvout, uuin, vvin, lat, lon)
+
+    def gdwdfuv(self, gdid, spd, wd, uuin, vvin, lat, lon):
+        return self._pts6(self.lib.c_gdwdfuv, gdid, spd, wd, uuin, vvin, lat, lon)
+
+    def gduvfwd(self, gdid, uuout, vvout, spd, wd, lat, lon):
+        return self._pts6(self.lib.c_gduvfwd, gdid, uuout, vvout, spd, wd, lat, lon)
 
     def gdsetmask(self, gdid, mask):
         return self.lib.c_gdsetmask(gdid, _ptr(np.ascontiguousarray(mask, dtype=np.int32)))

@@ -193,9 +193,71 @@ __global__ void __launch_bounds__(TPB) k_ll2xy_points(GridDev g, int njs, const 
     y[k] = py;
 }
 
+// caller-supplied points: (x, y) -> (lat, lon)   [c_gdllfxy, gdllfxy.c:30-92: 'U' grids split by y > nj of the Yin panel]
+__global__ void __launch_bounds__(TPB) k_xy2ll_points(GridDev g, GridDev g2, int is_u, const float *__restrict__ x, const float *__restrict__ y,
+                                                       float *__restrict__ lat, float *__restrict__ lon, int npts) {
+    int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= npts) return;
+    float la, lo;
+    const float xf = x[k], yf = y[k];
+    if (!is_u) {
+        ez_xy2ll(g, xf, yf, 1, la, lo);
+    } else if (yf > (float)g.nj) {
+        ez_xy2ll(g2, xf, yf - (float)g.nj, 0, la, lo);
+    } else {
+        ez_xy2ll(g, xf, yf, 0, la, lo);
+    }
+    lat[k] = la;
+    lon[k] = lo;
+}
+
+// (lat, lon) -> (x, y) on a 'U' supergrid: both panels, then the selection of gdxyfll.c:199-236 (the mask-core bounds
+// are the reference's 0-based indices compared against 1-based coordinates, as written there)
+__global__ void __launch_bounds__(TPB) k_ll2xy_u(GridDev yin, GridDev yan, int4 myin, int4 myan, const float *__restrict__ lat,
+                                                  const float *__restrict__ lon, float *__restrict__ x, float *__restrict__ y, int npts) {
+    int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= npts) return;
+    const float la = lat[k];
+    float lo1 = lon[k], lo2 = lo1, xi, yi, xa, ya;
+    ez_ll2xy(yin, yin.j2, la, lo1, xi, yi);
+    ez_ll2xy(yan, yan.j2, la, lo2, xa, ya);
+    const float maxni = (float)yin.ni, maxnj = (float)yin.nj;
+    float xo, yo;
+    if (xi > maxni || xi < 1.0f || yi > maxnj || yi < 1.0f) { xo = xa; yo = ya + maxnj; }
+    else { xo = xi; yo = yi; }
+    if (xa >= (float)myan.x && xa <= (float)myan.y && ya >= (float)myan.z && ya <= (float)myan.w) { xo = xa; yo = ya + maxnj; }
+    if (xi >= (float)myin.x && xi <= (float)myin.y && yi >= (float)myin.z && yi <= (float)myin.w) { xo = xi; yo = yi; }
+    x[k] = xo;
+    y[k] = yo;
+}
+
+// split 'U' coordinates into a panel bit and the y inside the panel (gdxysval.c:70-81)
+__global__ void __launch_bounds__(TPB) k_split_u(const float *__restrict__ y, int njyin, float *__restrict__ ty, uint8_t *__restrict__ zb, int npts) {
+    int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= npts) return;
+    const float yf = y[k];
+    const bool yang = yf > (float)njyin;
+    ty[k] = yang ? yf - (float)njyin : yf;
+    zb[k] = yang ? ZB_YANG : 0;
+}
+
 }  // namespace
 
 namespace ezk {
+void xy2ll_points(const GridDev &g, const GridDev &g2, int is_u, const float *x, const float *y, float *lat, float *lon, int npts, cudaStream_t s) {
+    if (npts <= 0) return;
+    k_xy2ll_points<<<nblocks(npts), TPB, 0, s>>>(g, g2, is_u, x, y, lat, lon, npts);
+}
+void ll2xy_u(const GridDev &yin, const GridDev &yan, const int myin[4], const int myan[4], const float *lat, const float *lon, float *x, float *y,
+             int npts, cudaStream_t s) {
+    if (npts <= 0) return;
+    k_ll2xy_u<<<nblocks(npts), TPB, 0, s>>>(yin, yan, make_int4(myin[0], myin[1], myin[2], myin[3]), make_int4(myan[0], myan[1], myan[2], myan[3]),
+                                            lat, lon, x, y, npts);
+}
+void split_u(const float *y, int njyin, float *ty, uint8_t *zb, int npts, cudaStream_t s) {
+    if (npts <= 0) return;
+    k_split_u<<<nblocks(npts), TPB, 0, s>>>(y, njyin, ty, zb, npts);
+}
 
 void calclatlon(const GridDev &g, float *lat, float *lon, int npts, cudaStream_t s) {
     if (npts <= 0) return;

@@ -228,3 +228,55 @@ __device__ __forceinline__ void ez_ll2xy(const GridDev &g, int njs, float lat, f
             return;
     }
 }
+
+// (x, y) in a grid's own index space -> true (lat, lon): c_gdllfxy_orig (gdllfxy.c:251-386) ; with newstyle != 0 the
+// y inversion of c_gdllfxy_new (gdllfxy.c:185-190) for Z/#/G grids whose ig2 == 1.
+__device__ __forceinline__ void ez_xy2ll(const GridDev &g, float xf, float yf, int newstyle, float &lat, float &lon) {
+    lat = 0.f;
+    lon = 0.f;
+    switch (g.grtyp) {
+        case 'A': case 'B': case 'L':
+            lat = (float)(((double)yf - 1.0) * (double)g.xg[2] + (double)g.xg[0]);
+            lon = (float)(((double)xf - 1.0) * (double)g.xg[3] + (double)g.xg[1]);
+            lon = (float)fmod((double)lon + 360.0, 360.0);
+            break;
+        case 'E': {
+            const float dlat = (float)(180.0 / (double)g.nj), dlon = (float)(360.0 / (double)(g.ni - 1));
+            const float swlat = (float)(-90.0 + 0.5 * (double)dlat), swlon = 0.0f;
+            const float tx = (float)(((double)xf - 1.0) * (double)dlon + (double)swlon);
+            const float ty = (float)(((double)yf - 1.0) * (double)dlat + (double)swlat);
+            ez_rotate_ll(g.ri, tx, ty, lon, lat);
+            break;
+        }
+        case 'N': case 'S':
+            ez_vllfxy1(lat, lon, xf, yf, g.xg[2], g.xg[3], g.xg[0], g.xg[1], g.hemisphere);
+            lon = (float)fmod((double)lon + 360.0, 360.0);
+            break;
+        case '#': case 'Z': case 'G': {
+            float yt = yf;
+            if (newstyle && g.ig[1] == 1) yt = (float)((double)g.nj + 1.0 - (double)yf);
+            int indx = (int)xf - 1, indy = (int)yt - 1;
+            indx = indx < 0 ? 0 : indx;
+            indy = indy < 0 ? 0 : indy;
+            indx = indx > g.ni - 2 ? g.ni - 2 : indx;
+            indy = indy > g.j2 - 2 ? g.j2 - 2 : indy;
+            const float delxx = __ldg(g.ax + indx + 1) - __ldg(g.ax + indx);
+            const float tx = (float)((double)__ldg(g.ax + indx) + (((double)xf - 1.0 - (double)indx) * (double)delxx));
+            const float delyy = __ldg(g.ay + indy + 1) - __ldg(g.ay + indy);
+            const float ty = (float)((double)__ldg(g.ay + indy) + (((double)yt - 1.0 - (double)indy) * (double)delyy));
+            if (g.grref == 'E') {
+                ez_rotate_ll(g.ri, tx, ty, lon, lat);
+            } else if (g.grref == 'N' || g.grref == 'S') {
+                ez_vllfxy1(lat, lon, tx, ty, g.xgref[2], g.xgref[3], g.xgref[0], g.xgref[1], g.hemisphere);
+                lon = (float)fmod((double)lon + 360.0, 360.0);
+            } else if (g.grref == 'L') {
+                lat = ty * g.xgref[2] + g.xgref[0];
+                lon = tx * g.xgref[3] + g.xgref[1];
+                lon = (float)fmod((double)lon + 360.0, 360.0);
+            }
+            break;
+        }
+        default: break;
+    }
+}
+

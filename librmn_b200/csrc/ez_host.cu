@@ -116,6 +116,7 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     DevBuf pipe_in[2], pipe_out[2];
+    DevBuf st_pts[10];          // staging of caller arrays in the scattered-point API
     DevBuf prow[2];             // synthetic pole rows of (u, v) for the polar vector correction (K18)
 };
 thread_local Session S;
@@ -1327,58 +1328,298 @@ int32_t c_gdll(int32_t gdid, float *lat, float *lon) {   // gdll.c:25-73
 }
 int32_t gdll_(int32_t *gdid, float *lat, float *lon) { return c_gdll(*gdid, lat, lon); }
 
-// c_gdxyfll for plain grids (gdxyfll.c:29-129; the 'U' selection logic of :190-243 is a "next" row, N1)
-int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int32_t n) {
+// ---- scattered-point API: the same kernels on caller-supplied points -------------------------
+namespace {
+// stages up to 10 caller arrays (host or device) for one call
+struct PtStage {
+    Staged st[10];
+    int n = 0;
+    bool ok = true;
+    float *in(const float *p, size_t cnt) {
+        if (n >= 10 || stage_in(st[n], S.st_pts[n], p, cnt) < 0) { ok = false; return nullptr; }
+        return st[n++].dev;
+    }
+    float *out(float *p, size_t cnt) {
+        if (n >= 10 || stage_out(st[n], S.st_pts[n], p, cnt) < 0) { ok = false; return nullptr; }
+        return st[n++].dev;
+    }
+    float *tmp(size_t cnt) {
+        if (n >= 10) { ok = false; return nullptr; }
+        float *d = (float *)S.st_pts[n].get(cnt * sizeof(float));
+        if (!d) ok = false;
+        n++;
+        return d;
+    }
+    int finish() {
+        for (int k = 0; k < n; k++)
+            if (finish_out(st[k]) < 0) return -1;
+        return 0;
+    }
+};
+
+// (lat, lon) -> (x, y) on device pointers: c_gdxyfll (gdxyfll.c:190-243)
+int xyfll_dev(Grid &g, float *d_x, float *d_y, const float *d_lat, const float *d_lon, int n) {
+    if (g.grtyp == 'Y') {
+        fprintf(stderr, "<c_gdxyfll> 'Y' grids are not supported by this entry point\n");
+        return -1;
+    }
+    if (g.nsubgrids > 0) {
+        Grid *yin = grid_of(g.subgrid[0]), *yan = grid_of(g.subgrid[1]);
+        if (!yin || !yan || ensure_device(*yin) < 0 || ensure_device(*yan) < 0) return -1;
+        const int myin[4] = {yin->mi0, yin->mi1, yin->mj0, yin->mj1}, myan[4] = {yan->mi0, yan->mi1, yan->mj0, yan->mj1};
+        ezk::ll2xy_u(to_dev(*yin), to_dev(*yan), myin, myan, d_lat, d_lon, d_x, d_y, n, S.stream);
+    } else {
+        if (ensure_device(g) < 0) return -1;
+        ezk::ll2xy_points(to_dev(g), g.j2, d_lat, d_lon, d_x, d_y, n, S.stream);
+    }
+    S.launches++;
+    return 0;
+}
+
+// c_gdxysint (gdxysint.c:30-54) on device pointers, one field; 'U' sources are split by y (gdxysval.c:50-100)
+int xysint_dev(Grid &g, float *d_zout, const float *d_zin, const float *d_x, const float *d_y, int n, int vector, int sym_sign) {
+    if (check_degree() < 0) return -1;
+    if (g.grtyp == 'Y') {
+        fprintf(stderr, "<c_gdxysval> 'Y' cloud sources are outside the hot-path scope (SURVEY.md 8f N2)\n");
+        return -1;
+    }
+    InterpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.zin = d_zin; a.zout = d_zout;
+    a.in_stride = (long)g.ni * g.nj; a.out_stride = n;
+    a.nfields = 1; a.npts = n;
+    a.o = snapshot_opts(vector, sym_sign);
+    a.x = d_x; a.y = d_y;
+    if (g.nsubgrids > 0) {
+        Grid *yin = grid_of(g.subgrid[0]), *yan = grid_of(g.subgrid[1]);
+        if (!yin || !yan || ensure_device(*yin) < 0 || ensure_device(*yan) < 0) return -1;
+        float *ty = (float *)S.st_misc[2].get((size_t)n * sizeof(float));
+        uint8_t *zb = (uint8_t *)S.st_scratch.get((size_t)n);
+        if (!ty || !zb) return -1;
+        ezk::split_u(d_y, yin->nj, ty, zb, n, S.stream);
+        S.launches++;
+        a.src = to_dev(*yin); a.src2 = to_dev(*yan);
+        a.yy = 1;
+        a.panel_stride = (long)yin->ni * yin->nj;
+        a.y = ty; a.zb = zb;
+    } else {
+        if (ensure_device(g) < 0) return -1;
+        a.src = to_dev(g);
+    }
+    S.last_path = 1;
+    S.launches += ezk::interp(a, S.stream);
+    return 0;
+}
+
+int wind_points_dev(Grid &g, float *d_u, float *d_v, const float *d_lat, const float *d_lon, const uint8_t *zb, int n, int mode) {
+    WindArgs w;
+    memset(&w, 0, sizeof(w));
+    if (g.nsubgrids > 0) {
+        w.src = to_dev(*grid_of(g.subgrid[0]));
+        w.src2 = to_dev(*grid_of(g.subgrid[1]));
+        w.yy = 1;
+        w.zb = zb;
+    } else {
+        w.src = to_dev(g);
+    }
+    w.dst = w.src;   // mode 1 uses src only, mode 2 uses dst only
+    w.lat = d_lat; w.lon = d_lon;
+    w.u = d_u; w.v = d_v;
+    w.stride = n; w.nfields = 1; w.npts = n; w.mode = mode;
+    ezk::wind(w, S.stream);
+    S.launches++;
+    return 0;
+}
+}  // namespace
+
+int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int32_t n) {   // gdxyfll.c:190-243
     std::lock_guard<std::recursive_mutex> lk(g_mtx);
     Grid *g = grid_of(gdid);
     if (!g || n < 0) return -1;
-    if (g->nsubgrids > 0 || g->grtyp == 'Y') {
-        fprintf(stderr, "<c_gdxyfll> 'U' and 'Y' grids are not supported by this entry point yet\n");
-        return -1;
-    }
     if (n == 0) return 0;
-    if (ensure_device(*g) < 0) return -1;
-    Staged sla, slo, sx, sy;
-    if (stage_in(sla, S.st_in[0], lat, n) < 0 || stage_in(slo, S.st_in[1], lon, n) < 0) return -1;
-    if (stage_out(sx, S.st_out[0], x, n) < 0 || stage_out(sy, S.st_out[1], y, n) < 0) return -1;
-    ezk::ll2xy_points(to_dev(*g), g->j2, sla.dev, slo.dev, sx.dev, sy.dev, n, S.stream);
-    S.launches++;
-    if (finish_out(sx) < 0 || finish_out(sy) < 0) return -1;
-    return 0;
+    PtStage p;
+    float *dla = p.in(lat, n), *dlo = p.in(lon, n), *dx = p.out(x, n), *dy = p.out(y, n);
+    if (!p.ok || xyfll_dev(*g, dx, dy, dla, dlo, n) < 0) return -1;
+    return p.finish();
 }
 int32_t gdxyfll_(int32_t *gdid, float *x, float *y, float *lat, float *lon, int32_t *n) { return c_gdxyfll(*gdid, x, y, lat, lon, *n); }
 
-// c_gdxysval (gdxysval.c:50-116): interpolate at caller-supplied x,y, no zone correction
-int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n) {
+int32_t c_gdllfxy(int32_t gdid, float *lat, float *lon, float *x, float *y, int32_t n) {   // gdllfxy.c:30-92
     std::lock_guard<std::recursive_mutex> lk(g_mtx);
-    Grid *g = grid_of(gdin);
-    if (!g || n < 0 || check_degree() < 0) return -1;
-    if (g->grtyp == 'Y') return -1;
-    if (n == 0) return 0;
-    Grid *yin = g->nsubgrids > 0 ? grid_of(g->subgrid[0]) : g;
-    Grid *yan = g->nsubgrids > 0 ? grid_of(g->subgrid[1]) : nullptr;
-    if (ensure_device(*yin) < 0 || (yan && ensure_device(*yan) < 0)) return -1;
-    size_t nin = (size_t)g->ni * g->nj;
-    Staged sz, sx, sy, so;
-    if (stage_in(sz, S.st_in[0], zin, nin) < 0 || stage_in(sx, S.st_in[1], x, n) < 0 || stage_in(sy, S.st_misc[2], y, n) < 0) return -1;
-    if (stage_out(so, S.st_out[0], zout, n) < 0) return -1;
-    InterpArgs a;
-    memset(&a, 0, sizeof(a));
-    a.src = to_dev(*yin);
-    a.x = sx.dev; a.y = sy.dev;
-    a.zin = sz.dev; a.zout = so.dev;
-    a.in_stride = (long)nin; a.out_stride = n;
-    a.nfields = 1; a.npts = n;
-    a.o = snapshot_opts(0, 1);
-    if (yan) {
-        fprintf(stderr, "<c_gdxysval> 'U' sources are not supported by this entry point yet\n");
+    Grid *g = grid_of(gdid);
+    if (!g || n < 0) return -1;
+    if (g->grtyp == 'Y') {
+        fprintf(stderr, "<gdllfxy>: This operation is not supported for 'Y' grids\n");
         return -1;
     }
-    S.launches += ezk::interp(a, S.stream);
-    if (finish_out(so) < 0) return -1;
-    return 0;
+    if (n == 0) return 0;
+    Grid *a = g->nsubgrids > 0 ? grid_of(g->subgrid[0]) : g, *b = g->nsubgrids > 0 ? grid_of(g->subgrid[1]) : g;
+    if (!a || !b || ensure_device(*a) < 0 || ensure_device(*b) < 0) return -1;
+    PtStage p;
+    float *dx = p.in(x, n), *dy = p.in(y, n), *dla = p.out(lat, n), *dlo = p.out(lon, n);
+    if (!p.ok) return -1;
+    ezk::xy2ll_points(to_dev(*a), to_dev(*b), g->nsubgrids > 0, dx, dy, dla, dlo, n, S.stream);
+    S.launches++;
+    return p.finish();
+}
+int32_t gdllfxy_(int32_t *gdid, float *lat, float *lon, float *x, float *y, int32_t *n) { return c_gdllfxy(*gdid, lat, lon, x, y, *n); }
+
+int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n) {   // gdxysval.c:50-116
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdin);
+    if (!g || n < 0) return -1;
+    if (n == 0) return 0;
+    PtStage p;
+    float *dz = p.in(zin, (size_t)g->ni * g->nj), *dx = p.in(x, n), *dy = p.in(y, n), *dout = p.out(zout, n);
+    if (!p.ok || xysint_dev(*g, dout, dz, dx, dy, n, 0, 1) < 0) return -1;
+    return p.finish();
 }
 int32_t gdxysval_(int32_t *gdin, float *zout, float *zin, float *x, float *y, int32_t *n) { return c_gdxysval(*gdin, zout, zin, x, y, *n); }
+
+int32_t c_gdllsval(int32_t gdid, float *zout, float *zin, float *lat, float *lon, int32_t n) {   // gdllsval.c:35-55
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g || n < 0) return -1;
+    if (n == 0) return 0;
+    PtStage p;
+    float *dz = p.in(zin, (size_t)g->ni * g->nj), *dla = p.in(lat, n), *dlo = p.in(lon, n), *dout = p.out(zout, n);
+    float *dx = p.tmp(n), *dy = p.tmp(n);
+    if (!p.ok || xyfll_dev(*g, dx, dy, dla, dlo, n) < 0 || xysint_dev(*g, dout, dz, dx, dy, n, 0, 1) < 0) return -1;
+    if (p.finish() < 0) return -1;
+    return 0;
+}
+int32_t gdllsval_(int32_t *gdid, float *zout, float *zin, float *lat, float *lon, int32_t *n) { return c_gdllsval(*gdid, zout, zin, lat, lon, *n); }
+
+// c_gdxyvval (gdxyvval.c:38-116): both components at caller-supplied x, y, as GRID components (no rotation)
+int32_t c_gdxyvval(int32_t gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdin);
+    if (!g || n < 0) return -1;
+    if (n == 0) return 0;
+    const size_t nin = (size_t)g->ni * g->nj;
+    PtStage p;
+    float *du = p.in(uuin, nin), *dv = p.in(vvin, nin), *dx = p.in(x, n), *dy = p.in(y, n), *ou = p.out(uuout, n), *ov = p.out(vvout, n);
+    if (!p.ok || xysint_dev(*g, ou, du, dx, dy, n, 1, +1) < 0 || xysint_dev(*g, ov, dv, dx, dy, n, 1, -1) < 0) return -1;
+    return p.finish();
+}
+int32_t gdxyvval_(int32_t *gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t *n) {
+    return c_gdxyvval(*gdin, uuout, vvout, uuin, vvin, x, y, *n);
+}
+
+int32_t c_gdllvval(int32_t gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t n) {   // gdllvval.c:37-58
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g || n < 0) return -1;
+    if (g->nsubgrids > 0) {
+        fprintf(stderr, "<gdllvval>: This operation is not supported for 'U' grids\n");
+        return -1;
+    }
+    if (n == 0) return 0;
+    const size_t nin = (size_t)g->ni * g->nj;
+    PtStage p;
+    float *du = p.in(uuin, nin), *dv = p.in(vvin, nin), *dla = p.in(lat, n), *dlo = p.in(lon, n), *ou = p.out(uuout, n), *ov = p.out(vvout, n);
+    float *dx = p.tmp(n), *dy = p.tmp(n);
+    if (!p.ok || xyfll_dev(*g, dx, dy, dla, dlo, n) < 0) return -1;
+    if (xysint_dev(*g, ou, du, dx, dy, n, 1, +1) < 0 || xysint_dev(*g, ov, dv, dx, dy, n, 1, -1) < 0) return -1;
+    if (p.finish() < 0) return -1;
+    return 0;
+}
+int32_t gdllvval_(int32_t *gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t *n) {
+    return c_gdllvval(*gdid, uuout, vvout, uuin, vvin, lat, lon, *n);
+}
+
+// c_gdwdfuv (gdwdfuv.c:100-113) / c_gduvfwd (gduvfwd.c:112-125): wind conversions at caller-supplied lat/lon
+int32_t c_gdwdfuv(int32_t gdid, float *spd_out, float *wd_out, float *uuin, float *vvin, float *latin, float *lonin, int32_t npts) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g || npts < 0) return -1;
+    if (g->nsubgrids > 0) {
+        fprintf(stderr, "<gdwdfuv>: This operation is not supported for 'U' grids\n");
+        return -1;
+    }
+    if (npts == 0) return 0;
+    PtStage p;
+    float *dla = p.in(latin, npts), *dlo = p.in(lonin, npts), *du = p.in(uuin, npts), *dv = p.in(vvin, npts);
+    float *os = p.out(spd_out, npts), *ow = p.out(wd_out, npts);
+    if (!p.ok) return -1;
+    if (os != du) CUDA_OK(cudaMemcpyAsync(os, du, (size_t)npts * sizeof(float), cudaMemcpyDeviceToDevice, S.stream));
+    if (ow != dv) CUDA_OK(cudaMemcpyAsync(ow, dv, (size_t)npts * sizeof(float), cudaMemcpyDeviceToDevice, S.stream));
+    if (wind_points_dev(*g, os, ow, dla, dlo, nullptr, npts, 1) < 0) return -1;
+    return p.finish();
+}
+int32_t gdwdfuv_(int32_t *gdid, float *spd_out, float *wd_out, float *uuin, float *vvin, float *latin, float *lonin, int32_t *npts) {
+    return c_gdwdfuv(*gdid, spd_out, wd_out, uuin, vvin, latin, lonin, *npts);
+}
+int32_t c_gduvfwd(int32_t gdid, float *uugdout, float *vvgdout, float *uullin, float *vvllin, float *latin, float *lonin, int32_t npts) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g || npts < 0) return -1;
+    if (g->nsubgrids > 0) {
+        fprintf(stderr, "<gduvfwd>: This operation is not supported for 'U' grids\n");
+        return -1;
+    }
+    if (npts == 0) return 0;
+    PtStage p;
+    float *dla = p.in(latin, npts), *dlo = p.in(lonin, npts), *ds = p.in(uullin, npts), *dw = p.in(vvllin, npts);
+    float *ou = p.out(uugdout, npts), *ov = p.out(vvgdout, npts);
+    if (!p.ok) return -1;
+    if (ou != ds) CUDA_OK(cudaMemcpyAsync(ou, ds, (size_t)npts * sizeof(float), cudaMemcpyDeviceToDevice, S.stream));
+    if (ov != dw) CUDA_OK(cudaMemcpyAsync(ov, dw, (size_t)npts * sizeof(float), cudaMemcpyDeviceToDevice, S.stream));
+    if (wind_points_dev(*g, ou, ov, dla, dlo, nullptr, npts, 2) < 0) return -1;
+    return p.finish();
+}
+int32_t gduvfwd_(int32_t *gdid, float *uugdout, float *vvgdout, float *uullin, float *vvllin, float *latin, float *lonin, int32_t *npts) {
+    return c_gduvfwd(*gdid, uugdout, vvgdout, uullin, vvllin, latin, lonin, *npts);
+}
+
+// c_gdxywdval (gdxywdval.c:38) / c_gdllwdval (gdllwdval.c:36-80): grid components at the points, then (speed, direction)
+namespace {
+int wdval_common(Grid &g, float *ou, float *ov, const float *du, const float *dv, const float *dx, const float *dy, const float *dla, const float *dlo,
+                 int n) {
+    if (xysint_dev(g, ou, du, dx, dy, n, 1, +1) < 0 || xysint_dev(g, ov, dv, dx, dy, n, 1, -1) < 0) return -1;
+    const uint8_t *zb = nullptr;
+    if (g.nsubgrids > 0) zb = (const uint8_t *)S.st_scratch.p;   // the panel bits xysint_dev just produced from y
+    return wind_points_dev(g, ou, ov, dla, dlo, zb, n, 1);
+}
+}  // namespace
+int32_t c_gdllwdval(int32_t gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdid);
+    if (!g || n < 0) return -1;
+    if (n == 0) return 0;
+    const size_t nin = (size_t)g->ni * g->nj;
+    PtStage p;
+    float *du = p.in(uuin, nin), *dv = p.in(vvin, nin), *dla = p.in(lat, n), *dlo = p.in(lon, n), *ou = p.out(uuout, n), *ov = p.out(vvout, n);
+    float *dx = p.tmp(n), *dy = p.tmp(n);
+    if (!p.ok || xyfll_dev(*g, dx, dy, dla, dlo, n) < 0 || wdval_common(*g, ou, ov, du, dv, dx, dy, dla, dlo, n) < 0) return -1;
+    if (p.finish() < 0) return -1;
+    return 0;
+}
+int32_t gdllwdval_(int32_t *gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t *n) {
+    return c_gdllwdval(*gdid, uuout, vvout, uuin, vvin, lat, lon, *n);
+}
+int32_t c_gdxywdval(int32_t gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Grid *g = grid_of(gdin);
+    if (!g || n < 0) return -1;
+    if (g->grtyp == 'Y') return -1;
+    if (n == 0) return 0;
+    const size_t nin = (size_t)g->ni * g->nj;
+    Grid *a = g->nsubgrids > 0 ? grid_of(g->subgrid[0]) : g, *b = g->nsubgrids > 0 ? grid_of(g->subgrid[1]) : g;
+    if (!a || !b || ensure_device(*a) < 0 || ensure_device(*b) < 0) return -1;
+    PtStage p;
+    float *du = p.in(uuin, nin), *dv = p.in(vvin, nin), *dx = p.in(x, n), *dy = p.in(y, n), *ou = p.out(uuout, n), *ov = p.out(vvout, n);
+    float *dla = p.tmp(n), *dlo = p.tmp(n);
+    if (!p.ok) return -1;
+    ezk::xy2ll_points(to_dev(*a), to_dev(*b), g->nsubgrids > 0, dx, dy, dla, dlo, n, S.stream);   // c_gdllfxy (gdxywdval.c)
+    S.launches++;
+    if (wdval_common(*g, ou, ov, du, dv, dx, dy, dla, dlo, n) < 0) return -1;
+    if (p.finish() < 0) return -1;
+    return 0;
+}
+int32_t gdxywdval_(int32_t *gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t *n) {
+    return c_gdxywdval(*gdin, uuout, vvout, uuin, vvin, x, y, *n);
+}
 
 int c_gdsetmask(int gdid, int *mask) {
     std::lock_guard<std::recursive_mutex> lk(g_mtx);

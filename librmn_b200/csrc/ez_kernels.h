@@ -63,6 +63,11 @@ void calcxy(const GridDev &src, int njs, const float *lat, float *lon, int write
 void yy_calcxy(const GridDev &maskgrid, const GridDev &yin, const GridDev &yan, int use_mask, const float *lat, const float *lon,
                float *x, float *y, uint8_t *zb, unsigned int *counts, int npts, cudaStream_t s);
 void ll2xy_points(const GridDev &g, int njs, const float *lat, const float *lon, float *x, float *y, int npts, cudaStream_t s);
+// scattered-point API: inverse transform, 'U' supergrid selection, 'U' panel split
+void xy2ll_points(const GridDev &g, const GridDev &g2, int is_u, const float *x, const float *y, float *lat, float *lon, int npts, cudaStream_t s);
+void ll2xy_u(const GridDev &yin, const GridDev &yan, const int myin[4], const int myan[4], const float *lat, const float *lon, float *x, float *y,
+             int npts, cudaStream_t s);
+void split_u(const float *y, int njyin, float *ty, uint8_t *zb, int npts, cudaStream_t s);
 
 // K10 pre-pass: per-field pole-row means (sequential fp32 sums, bit-faithful to ez_calcpoleval) and min/max.
 void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s);

@@ -150,44 +150,9 @@ __global__ void __launch_bounds__(TPB) k_wind(WindArgs a) {
 //   direction_i = direction_pole +/- lon_i, same speed ; -> (u, v) on the 'A' grid = the pole row (:106-114)
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void src_point_lonlat(const GridDev &g, int i, int y, float &plon, float &plat) {
-    // c_gdllfxy_orig(gdin, lat, lon, x = i + 1, y), gdllfxy.c:251-386 ; then ez_gfxyfll for Z/E (ez_calcnpolarwind.c:70-83)
-    const float xf = (float)(i + 1), yf = (float)y;
-    float lon = 0.f, lat = 0.f;
-    switch (g.grtyp) {
-        case 'A': case 'B': case 'L':
-            lat = (float)(((double)yf - 1.0) * (double)g.xg[2] + (double)g.xg[0]);
-            lon = (float)(((double)xf - 1.0) * (double)g.xg[3] + (double)g.xg[1]);
-            lon = (float)fmod((double)lon + 360.0, 360.0);
-            break;
-        case 'E': {
-            const float dlat = (float)(180.0 / (double)g.nj), dlon = (float)(360.0 / (double)(g.ni - 1));
-            const float swlat = (float)(-90.0 + 0.5 * (double)dlat), swlon = 0.0f;
-            const float tx = (float)(((double)xf - 1.0) * (double)dlon + (double)swlon);
-            const float ty = (float)(((double)yf - 1.0) * (double)dlat + (double)swlat);
-            ez_rotate_ll(g.ri, tx, ty, lon, lat);
-            break;
-        }
-        case '#': case 'Z': case 'G': {
-            int indx = (int)xf - 1, indy = (int)yf - 1;
-            indx = indx < 0 ? 0 : indx;
-            indy = indy < 0 ? 0 : indy;
-            indx = indx > g.ni - 2 ? g.ni - 2 : indx;
-            indy = indy > g.j2 - 2 ? g.j2 - 2 : indy;
-            const float delxx = __ldg(g.ax + indx + 1) - __ldg(g.ax + indx);
-            const float tx = (float)((double)__ldg(g.ax + indx) + (((double)xf - 1.0 - (double)indx) * (double)delxx));
-            const float delyy = __ldg(g.ay + indy + 1) - __ldg(g.ay + indy);
-            const float ty = (float)((double)__ldg(g.ay + indy) + (((double)yf - 1.0 - (double)indy) * (double)delyy));
-            if (g.grref == 'E') {
-                ez_rotate_ll(g.ri, tx, ty, lon, lat);
-            } else if (g.grref == 'L') {
-                lat = ty * g.xgref[2] + g.xgref[0];
-                lon = tx * g.xgref[3] + g.xgref[1];
-                lon = (float)fmod((double)lon + 360.0, 360.0);
-            }
-            break;
-        }
-        default: break;
-    }
+    // c_gdllfxy_orig(gdin, lat, lon, x = i + 1, y) ; then ez_gfxyfll for Z/E (ez_calcnpolarwind.c:70-83)
+    float lon, lat;
+    ez_xy2ll(g, (float)(i + 1), (float)y, 0, lat, lon);
     if (g.grtyp == 'Z' && g.grref == 'E') {
         float lr, ar;
         ez_rotate_ll(g.r, lon, lat, lr, ar);
