@@ -48,7 +48,9 @@ struct TilePlan {   // classification of the target points for the tiled kernel 
     TileDesc *d_tiles = nullptr;
     uint32_t *d_flags = nullptr;
     int *d_list = nullptr;
+    unsigned int *d_rowy = nullptr;   // row-separable tiles: y of each target row (ez_interp_rowsep.cuh)
     int nlist = 0, ntiles_fast = 0, cap = 0;
+    int ntiles_rowsep = 0, vw = 0, cap_rs = 0;
 };
 
 struct Gset {   // _gridset, ez_def.h:148-166, device-resident
@@ -109,7 +111,7 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     cudaStream_t stream = 0;
     int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
-    int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 tiled, 4 per-point on the compacted list
+    int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 window tile kernel, 4 per-point on the compacted list, 8 row-separable tile kernel
     int last_nlist = 0;
     DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4];
     // host-pointer pipeline (ezsint_pipelined): two copy streams beside the compute stream, double-buffered chunks
@@ -635,18 +637,22 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     int ntx, nty;
     ezk::tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
     const size_t ntiles = (size_t)ntx * nty;
-    unsigned int *d_counters = (unsigned int *)S.st_misc[3].get(4 * sizeof(unsigned int));
+    unsigned int *d_counters = (unsigned int *)S.st_misc[3].get(8 * sizeof(unsigned int));
     if (!d_counters) return nullptr;
     if (cudaMalloc((void **)&tp.d_tiles, ntiles * sizeof(TileDesc)) != cudaSuccess ||
-        cudaMalloc((void **)&tp.d_flags, ntiles * 8 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaMalloc((void **)&tp.d_flags, ntiles * 8 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&tp.d_rowy, ntiles * 32 * sizeof(unsigned int)) != cudaSuccess) {
         fprintf(stderr, "<ezb200> cudaMalloc failed for the tile plan: %s\n", cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
-    cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), S.stream);
-    ezk::tile_classify(a, tp.d_tiles, tp.d_flags, d_counters, S.stream);
+    cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), S.stream);
+    InterpArgs ca = a;
+    static const bool rowsep_on = !(getenv("EZB200_ROWSEP") && atoi(getenv("EZB200_ROWSEP")) == 0);
+    ca.rowsep_enable = (rowsep_on && (!a.yy || ((a.src.ni - a.src2.ni) & 3) == 0)) ? 1 : 0;   // one staged pitch for both panels
+    ezk::tile_classify(ca, tp.d_tiles, tp.d_flags, tp.d_rowy, d_counters, S.stream);
     S.launches++;
-    unsigned int hc[4] = {0, 0, 0, 0};
-    if (cudaMemcpyAsync(hc, d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+    unsigned int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyAsync(hc, d_counters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
         cudaStreamSynchronize(S.stream) != cudaSuccess) {
         fprintf(stderr, "<ezb200> tile classification failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return nullptr;
@@ -654,6 +660,9 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     tp.nlist = (int)hc[0];
     tp.ntiles_fast = (int)hc[1];
     tp.cap = ((int)hc[2] + 3) & ~3;   // floats per staged level: the largest tile box, 16-byte granular
+    tp.vw = (int)hc[3];
+    tp.ntiles_rowsep = (int)hc[4];
+    tp.cap_rs = (int)hc[5];   // tallest row-separable box; ezk::interp turns it into floats per staged level
     // the tile kernel pays off when most points take it (target as fine as the source); otherwise keep the per-point kernel
     tp.suitable = tp.ntiles_fast > 0 && (size_t)tp.nlist * 2 <= (size_t)a.npts;
     if (tp.suitable && tp.nlist > 0) {
@@ -663,12 +672,12 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
         S.launches++;
     }
     if (!tp.suitable) {
-        cudaFree(tp.d_tiles); cudaFree(tp.d_flags);
-        tp.d_tiles = nullptr; tp.d_flags = nullptr;
+        cudaFree(tp.d_tiles); cudaFree(tp.d_flags); cudaFree(tp.d_rowy);
+        tp.d_tiles = nullptr; tp.d_flags = nullptr; tp.d_rowy = nullptr;
     }
     if (S.opt.verbose > 0)
-        fprintf(stderr, "<ezb200> tile plan: %d of %d points on the per-point list, %d of %zu tiles active, %s\n", tp.nlist, a.npts,
-                tp.ntiles_fast, ntiles, tp.suitable ? "tiled kernel" : "per-point kernel");
+        fprintf(stderr, "<ezb200> tile plan: %d of %d points on the per-point list, %d of %zu tiles active (%d row-separable), %s\n", tp.nlist,
+                a.npts, tp.ntiles_fast, ntiles, tp.ntiles_rowsep, tp.suitable ? "tiled kernels" : "per-point kernel");
     tp.built = true;
     return &tp;
 }
@@ -678,6 +687,7 @@ void free_gset(Gset &gs) {
         if (tp.d_tiles) cudaFree(tp.d_tiles);
         if (tp.d_flags) cudaFree(tp.d_flags);
         if (tp.d_list) cudaFree(tp.d_list);
+        if (tp.d_rowy) cudaFree(tp.d_rowy);
         tp = TilePlan();
     }
     if (gs.d_x) cudaFree(gs.d_x);
@@ -801,11 +811,16 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.tiles = tp->d_tiles;
             a.tile_flags = tp->d_flags;
             a.tile_cap = tp->cap;
+            a.tile_rowy = tp->d_rowy;
+            a.tile_vw = tp->vw;
+            a.tile_cap_rs = tp->cap_rs;
+            a.ntiles_rowsep = tp->ntiles_rowsep;
+            a.ntiles_window = tp->ntiles_fast - tp->ntiles_rowsep;
             a.list = tp->d_list;
             a.nlist = tp->nlist;
         }
     }
-    S.last_path = a.tiles ? (2 | (a.nlist > 0 ? 4 : 0)) : 1;
+    S.last_path = a.tiles ? ((a.ntiles_window > 0 ? 2 : 0) | (a.nlist > 0 ? 4 : 0) | (a.ntiles_rowsep > 0 ? 8 : 0)) : 1;
     S.last_nlist = a.tiles ? a.nlist : 0;
     S.launches += ezk::interp(a, S.stream);
     // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged

@@ -609,6 +609,7 @@ __global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj,
 
 #include "ez_interp_fast.cuh"
 #include "ez_interp_tiled.cuh"
+#include "ez_interp_rowsep.cuh"
 
 namespace ezk {
 
@@ -639,12 +640,12 @@ void tile_dims(int out_ni, int out_nj, int *ntx, int *nty) {
     *nty = (out_nj + TO - 1) / TO;
 }
 
-void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *counters, cudaStream_t s) {
+void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *rowy, unsigned int *counters, cudaStream_t s) {
     int ntx, nty;
     tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
     dim3 grid(ntx, nty);
-    if (a.o.degree == EZ_CUBIC) k_tile_classify<3><<<grid, TT * TT, 0, s>>>(a, tiles, flags, counters);
-    else k_tile_classify<1><<<grid, TT * TT, 0, s>>>(a, tiles, flags, counters);
+    if (a.o.degree == EZ_CUBIC) k_tile_classify<3><<<grid, TT * TT, 0, s>>>(a, tiles, flags, rowy, counters);
+    else k_tile_classify<1><<<grid, TT * TT, 0, s>>>(a, tiles, flags, rowy, counters);
 }
 
 void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s) {
@@ -657,20 +658,45 @@ void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned i
 int interp(const InterpArgs &a, cudaStream_t s) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
     if (a.tiles) {
-        // tiled path: the tile kernel for every point that fits, the per-point kernel for the compacted rest
-        int ntx, nty, launches = 1;
+        // tiled path: the two tile kernels for every point that fits, the per-point kernel for the compacted rest
+        int ntx, nty, launches = 0;
         tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
         dim3 grid(ntx, nty);
         const size_t smem = (size_t)NSTAGE * LPS * a.tile_cap * sizeof(float);
+        // row-separable kernel: staged pitch congruent to the source row length mod 4 (16-byte cp.async, ez_interp_rowsep.cuh)
+        const int rs_p = rs_pitch(a.src.ni);
+        InterpArgs ar = a;
+        ar.tile_cap_rs = rs_cap(rs_p, a.tile_cap_rs);   // a.tile_cap_rs arrives as the tallest box height
+        const size_t smem_rs = (size_t)RS_NSTAGE * LPS * ar.tile_cap_rs * sizeof(float) + 2 * (size_t)TO * RS_VP * sizeof(float4) + 64;
         static bool attr_set = false;
         if (!attr_set) {
             const int mx = NSTAGE * LPS * TILE_CAP * (int)sizeof(float);
             cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            const int mxr = RS_NSTAGE * LPS * (TILE_CAP + 16) * (int)sizeof(float) + 2 * TO * RS_VP * (int)sizeof(float4) + 64;
+#define EZ_RS_ATTR(P)                                                                                       \
+    cudaFuncSetAttribute(k_interp_rowsep<3, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxr); \
+    cudaFuncSetAttribute(k_interp_rowsep<1, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxr);
+            EZ_RS_ATTR(35) EZ_RS_ATTR(36) EZ_RS_ATTR(37) EZ_RS_ATTR(38)
+#undef EZ_RS_ATTR
             attr_set = true;
         }
-        if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
-        else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
+        if (a.ntiles_rowsep > 0) {
+            const bool cub = a.o.degree == EZ_CUBIC;
+#define EZ_RS_LAUNCH(P)                                                               \
+    case P:                                                                           \
+        if (cub) k_interp_rowsep<3, P><<<grid, RS_NTHR, smem_rs, s>>>(ar);   \
+        else k_interp_rowsep<1, P><<<grid, RS_NTHR, smem_rs, s>>>(ar);       \
+        break;
+            switch (rs_p) { EZ_RS_LAUNCH(35) EZ_RS_LAUNCH(36) EZ_RS_LAUNCH(37) EZ_RS_LAUNCH(38) }
+#undef EZ_RS_LAUNCH
+            launches++;
+        }
+        if (a.ntiles_window > 0) {
+            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
+            else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
+            launches++;
+        }
         if (a.nlist > 0) {
             InterpArgs b = a;
             b.tiles = nullptr;

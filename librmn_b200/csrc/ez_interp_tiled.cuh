@@ -85,11 +85,24 @@ __device__ __forceinline__ Quad quad_of_thread(int bx, int by) {
 // ---------------------------------------------------------------------------------------------------
 // classification (once per gridset, degree and zone setting)
 // ---------------------------------------------------------------------------------------------------
+// Per-thread result of the classification: `elig` = every valid point of the quad is zone-free, on the tile's panel and
+// has contiguous stencil columns; `fast` = elig and the four stencils fit one W x W window (what the 2x2 window kernel
+// needs); `rowpair` = the two target rows of the quad have stencil row origins at most one apart (what the
+// row-separable kernel needs).  (cmin..cmax, rmin..rmax) are the extents of the stencil ORIGINS.
+struct QuadClass {
+    bool elig, fast, rowpair;
+    int cmin, cmax, rmin, rmax;
+    unsigned int ybits[2];   // bit pattern of y of the quad's two target rows (valid when yok[r])
+    bool yok[2];             // row r has at least one valid point and all of them carry the same y
+};
 template <int DEG>
-__device__ __forceinline__ void classify_thread(const GridDev &g, const InterpArgs &a, const Quad &q, int tile_panel, bool &fast, int &wc0, int &wr0) {
+__device__ __forceinline__ QuadClass classify_thread(const GridDev &g, const InterpArgs &a, const Quad &q, int tile_panel) {
     const int ni = a.out_ni, nj = a.out_nj;
-    int cmin = INT_MAX, cmax = INT_MIN, rmin = INT_MAX, rmax = INT_MIN, nvalid = 0;
-    bool ok = true;
+    QuadClass k;
+    k.cmin = INT_MAX; k.cmax = INT_MIN; k.rmin = INT_MAX; k.rmax = INT_MIN;
+    k.yok[0] = k.yok[1] = false; k.ybits[0] = k.ybits[1] = 0u;
+    int nvalid = 0, rrow[2] = {INT_MAX, INT_MAX};
+    bool ok = true, ysame = true;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
         if (!q.valid(p, ni, nj)) continue;
@@ -100,48 +113,79 @@ __device__ __forceinline__ void classify_thread(const GridDev &g, const InterpAr
         if ((a.use_zones && (bits & 0x1f)) || panel != tile_panel) { ok = false; continue; }
         int c0, r0;
         float wx[4], wy[4], s;
-        if (!point_plan<DEG>(g, a.x[n], a.y[n], c0, r0, wx, wy, s)) ok = false;
-        cmin = min(cmin, c0); cmax = max(cmax, c0);
-        rmin = min(rmin, r0); rmax = max(rmax, r0);
+        const float py = a.y[n];
+        if (!point_plan<DEG>(g, a.x[n], py, c0, r0, wx, wy, s)) ok = false;
+        k.cmin = min(k.cmin, c0); k.cmax = max(k.cmax, c0);
+        k.rmin = min(k.rmin, r0); k.rmax = max(k.rmax, r0);
+        const int row = p >> 1;
+        const unsigned int yb = __float_as_uint(py);
+        if (k.yok[row] && k.ybits[row] != yb) ysame = false;
+        k.yok[row] = true; k.ybits[row] = yb;
+        rrow[row] = r0;
     }
-    fast = ok && nvalid > 0 && (cmax - cmin) <= 1 && (rmax - rmin) <= 1;
-    wc0 = cmin;
-    wr0 = rmin;
+    k.elig = ok && nvalid > 0;
+    k.fast = k.elig && (k.cmax - k.cmin) <= 1 && (k.rmax - k.rmin) <= 1;
+    k.rowpair = k.elig && ysame && (!(k.yok[0] && k.yok[1]) || abs(rrow[1] - rrow[0]) <= 1);
+    return k;
 }
+
+constexpr unsigned int ROWY_NONE = 0x7fc0dead;   // "this target row of the tile has no point on the row-separable path"
 
 template <int DEG>
 __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant__ InterpArgs a, TileDesc *__restrict__ tiles,
-                                                           uint32_t *__restrict__ flags, unsigned int *__restrict__ counters) {
-    __shared__ int s_box[4];
+                                                           uint32_t *__restrict__ flags, unsigned int *__restrict__ rowy,
+                                                           unsigned int *__restrict__ counters) {
+    __shared__ int s_box[8];          // [0..3] window-kernel box, [4..7] row-separable box
     __shared__ int s_cnt[2];
+    __shared__ unsigned int s_rowy[TO];
+    __shared__ int s_bad;             // some quad breaks the row-separable structure
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const Quad q = quad_of_thread(blockIdx.x, blockIdx.y);
     const int ni = a.out_ni, nj = a.out_nj;
-    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; s_cnt[0] = 0; s_cnt[1] = 0; }
+    if (threadIdx.x < 8) s_box[threadIdx.x] = (threadIdx.x & 2) ? INT_MIN : INT_MAX;
+    if (threadIdx.x < TO) s_rowy[threadIdx.x] = ROWY_NONE;
+    if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_bad = 0; }
     // panel of the tile: majority of the threads' first points
     const bool v0 = q.valid(0, ni, nj);
     const bool yang0 = v0 && a.yy && a.zb && (a.zb[q.index(0, ni)] & ZB_YANG);
     const int n_valid = __syncthreads_count(v0);
     const int n_yang = __syncthreads_count(yang0);
     const int tile_panel = (2 * n_yang > n_valid) ? 1 : 0;
-    bool fast;
-    int wc0, wr0;
-    if (tile_panel) classify_thread<DEG>(a.src2, a, q, 1, fast, wc0, wr0);
-    else classify_thread<DEG>(a.src, a, q, 0, fast, wc0, wr0);
-    if (fast) {
-        atomicMin(&s_box[0], wc0); atomicMin(&s_box[1], wr0);
-        atomicMax(&s_box[2], wc0 + Sten<DEG>::W - 1);
-        atomicMax(&s_box[3], wr0 + Sten<DEG>::W - 1);
+    const QuadClass k = tile_panel ? classify_thread<DEG>(a.src2, a, q, 1) : classify_thread<DEG>(a.src, a, q, 0);
+    constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
+    if (k.fast) {
+        atomicMin(&s_box[0], k.cmin); atomicMin(&s_box[1], k.rmin);
+        atomicMax(&s_box[2], k.cmin + W - 1);
+        atomicMax(&s_box[3], k.rmin + W - 1);
+    }
+    if (k.elig) {
+        // row-separable kernel: exact stencil columns, one zero-weight row of overhang for the row-pair window
+        atomicMin(&s_box[4], k.cmin); atomicMin(&s_box[5], k.rmin);
+        atomicMax(&s_box[6], k.cmax + S - 1);
+        atomicMax(&s_box[7], k.rmax + W - 1);
+        if (!k.rowpair) s_bad = 1;
+        const int row0 = 2 * (threadIdx.x >> 4);
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            if (k.yok[r]) {
+                const unsigned int old = atomicCAS(&s_rowy[row0 + r], ROWY_NONE, k.ybits[r]);
+                if (old != ROWY_NONE && old != k.ybits[r]) s_bad = 1;
+            }
     }
     __syncthreads();
-    const int c0 = s_box[0], r0 = s_box[1], c1 = s_box[2], r1 = s_box[3];
+    // row-separable tile: every eligible quad qualifies (same y along each target row) and the box fits
+    const int sc0 = s_box[4], sr0 = s_box[5], sw = s_box[6] - s_box[4] + 1, sh = s_box[7] - s_box[5] + 1;
+    const bool rowsep = a.rowsep_enable && !s_bad && sc0 != INT_MAX && sw <= 32 && sh <= 51 && 38L * sh + 8 <= TILE_CAP;
+    const int c0 = rowsep ? sc0 : s_box[0], r0 = rowsep ? sr0 : s_box[1];
+    const int c1 = rowsep ? s_box[6] : s_box[2], r1 = rowsep ? s_box[7] : s_box[3];
     // the box holds every fast thread's full window; a window may overhang the field by one column/row on the
     // high side (that column/row carries zero weights) -- stage_tile replicates the field edge there
     const int w = c1 - c0 + 1, h = r1 - r0 + 1;
     const bool box_ok = (c0 != INT_MAX) && w <= 64 && (long)(w | 1) * h <= TILE_CAP;
-    fast = fast && box_ok;
+    const bool fast = (rowsep ? k.elig : k.fast) && box_ok;
     const unsigned int ballot = __ballot_sync(0xffffffffu, fast);
     if ((threadIdx.x & 31) == 0) flags[tile * 8 + (threadIdx.x >> 5)] = ballot;
+    if (threadIdx.x < TO) rowy[tile * TO + threadIdx.x] = rowsep ? s_rowy[threadIdx.x] : ROWY_NONE;
     int nslow = 0;
     if (!fast)
         for (int p = 0; p < 4; p++) nslow += q.valid(p, ni, nj) ? 1 : 0;
@@ -151,11 +195,16 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     if (threadIdx.x == 0) {
         TileDesc td;
         td.c0 = box_ok ? c0 : 0; td.r0 = box_ok ? r0 : 0; td.w = box_ok ? w : 0; td.h = box_ok ? h : 0;
-        td.panel = tile_panel; td.nfast = s_cnt[1]; td.nslow = s_cnt[0]; td.pad = 0;
+        td.panel = tile_panel; td.nfast = s_cnt[1]; td.nslow = s_cnt[0]; td.kind = (rowsep && box_ok) ? 1 : 0;
         tiles[tile] = td;
         atomicAdd(counters + 0, (unsigned int)s_cnt[0]);
-        if (box_ok && s_cnt[1] > 0) atomicMax(counters + 2, (unsigned int)((w | 1) * h));
+        if (box_ok && s_cnt[1] > 0 && td.kind == 0) atomicMax(counters + 2, (unsigned int)((w | 1) * h));
         if (s_cnt[1] > 0) atomicAdd(counters + 1, 1u);
+        if (td.kind == 1 && s_cnt[1] > 0) {
+            atomicMax(counters + 3, (unsigned int)w);
+            atomicAdd(counters + 4, 1u);
+            atomicMax(counters + 5, (unsigned int)h);
+        }
     }
 }
 
@@ -195,7 +244,8 @@ __global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ I
 #endif
 constexpr int NPROD = EZ_NPROD;           // producer warps per CTA (each has its own limit of outstanding cp.async requests)
 constexpr int NTHR_TILED = TT * TT + 32 * NPROD;
-__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR_TILED) : "memory"); }
+template <int NTHR_BAR = NTHR_TILED>
+__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR_BAR) : "memory"); }
 
 // The producer warp: stages the tile's box of every source level into shared memory with cp.async (LDGSTS), one
 // level ahead of the compute warps.  Lane l copies box columns l and l+32 (boxes are at most 64 wide) of every box
@@ -212,11 +262,11 @@ __device__ __forceinline__ void stage_rows(float *__restrict__ dst, const float 
     }
 }
 
+template <int NTHR_BAR = NTHR_TILED>
 __device__ __forceinline__ void producer_warp(const InterpArgs &a, const float *__restrict__ zin, const TileDesc &td, int src_ni, int src_rows,
-                                              float *__restrict__ smem) {
+                                              float *__restrict__ smem, const int pitch, const int cap) {
     const int lane = threadIdx.x & 31;
-    const int pitch = td.w | 1;
-    const int pw = (threadIdx.x - TT * TT) >> 5;                    // this producer warp copies box rows pw, pw + NPROD, ...
+    const int pw = (threadIdx.x - (NTHR_BAR - 32 * NPROD)) >> 5;    // this producer warp copies box rows pw, pw + NPROD, ...
     const int nrow = (min(td.h, src_rows - td.r0) - pw + NPROD - 1) / NPROD;
     const bool c0ok = lane < td.w && (td.c0 + lane) < src_ni;
     const bool c1ok = (lane + 32) < td.w && (td.c0 + lane + 32) < src_ni;
@@ -225,7 +275,6 @@ __device__ __forceinline__ void producer_warp(const InterpArgs &a, const float *
     const long is = a.in_stride;
     // A stage holds LPS consecutive levels; the producer runs NSTAGE-1 stages ahead.  Empty commit groups keep the
     // group count uniform at the tail.
-    const int cap = a.tile_cap;
     const int nstages = (nf + LPS - 1) / LPS;
     auto stage = [&](int st) {
         if (st < nstages) {
@@ -242,7 +291,7 @@ __device__ __forceinline__ void producer_warp(const InterpArgs &a, const float *
     for (int k = 0; k < NSTAGE - 1; k++) stage(k);
     for (int st = 0; st < nstages; st++) {
         __pipeline_wait_prior(NSTAGE - 2);   // stage st has landed
-        tile_barrier();                      // ... and every compute warp is done with stage st-1, whose buffers are refilled next
+        tile_barrier<NTHR_BAR>();            // ... and every compute warp is done with stage st-1, whose buffers are refilled next
         stage(st + NSTAGE - 1);
     }
 }
@@ -357,12 +406,12 @@ __global__ void __launch_bounds__(NTHR_TILED, EZ_TILED_MINB) k_interp_tiled(cons
     const int by = remap_tile_row(blockIdx.y, gridDim.y);
     const int tile = by * gridDim.x + blockIdx.x;
     const TileDesc td = a.tiles[tile];
-    if (td.nfast == 0) return;
+    if (td.nfast == 0 || td.kind != 0) return;   // kind 1: the row-separable kernel owns the tile
     for (int k = threadIdx.x; k < NSTAGE * LPS * a.tile_cap; k += NTHR_TILED) smem[k] = 0.f;
     __syncthreads();
     if (threadIdx.x >= TT * TT) {
-        if (td.panel) producer_warp(a, a.zin + a.panel_stride, td, a.src2.ni, a.src2.j2 - a.src2.j1 + 1, smem);
-        else producer_warp(a, a.zin, td, a.src.ni, a.src.j2 - a.src.j1 + 1, smem);
+        if (td.panel) producer_warp(a, a.zin + a.panel_stride, td, a.src2.ni, a.src2.j2 - a.src2.j1 + 1, smem, td.w | 1, a.tile_cap);
+        else producer_warp(a, a.zin, td, a.src.ni, a.src.j2 - a.src.j1 + 1, smem, td.w | 1, a.tile_cap);
         return;
     }
     const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;

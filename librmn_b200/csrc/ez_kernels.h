@@ -27,6 +27,13 @@ struct InterpArgs {
     const TileDesc *tiles;
     const uint32_t *tile_flags;   // 8 words per tile: bit t = thread t takes the tile path
     int tile_cap;                 // floats reserved per staged source level (>= the largest tile box)
+    // row-separable kernel (ez_interp_rowsep.cuh): y of each target row of each tile (32 words per tile), width of the
+    // widest row-separable box, how many tiles take each of the two tile kernels
+    const unsigned int *tile_rowy;
+    int tile_vw;                  // widest row-separable box (<= 32: pitch-33 kernel, else pitch-65 kernel)
+    int tile_cap_rs;              // floats per staged source level in the row-separable kernel (pitch x tallest box)
+    int ntiles_rowsep, ntiles_window;
+    int rowsep_enable;            // classification only: allow tiles to be marked row-separable
     // per-point kernel restricted to a compacted list of target points (nullptr = all npts points)
     const int *list;
     int nlist;
@@ -76,7 +83,7 @@ int interp(const InterpArgs &a, cudaStream_t s);
 // tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry
 bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
-void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *counters, cudaStream_t s);
+void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *rowy, unsigned int *counters, cudaStream_t s);
 void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s);
 // K19 integer mask transfer
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,

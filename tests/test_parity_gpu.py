@@ -290,7 +290,7 @@ def test_tiled_kernel_against_oracle(ezb, ezref, cuda_ok, degree):
     for c_b, c_r in zip(medium_cases(ezb, degree), medium_cases(ezref, degree)):
         rc_b, out_b = cases.run_case(ezb, c_b)
         path, nlist = ezb.last_path()
-        assert path & 2, "%s did not take the tiled kernel (path=%d)" % (c_b.name, path)
+        assert path & 10, "%s did not take the tiled kernel (path=%d)" % (c_b.name, path)
         assert nlist < 0.35 * c_b.n_out, "%s: %d of %d points left to the per-point list" % (c_b.name, nlist, c_b.n_out)
         rc_r, out_r = cases.run_case(ezref, c_r)
         assert rc_b == rc_r, c_b.name
@@ -330,7 +330,7 @@ def test_tiled_kernel_equals_per_point_kernel(ezb, cuda_ok, degree):
             assert ezb.ezsint_batch(z, zin, nf) >= 0
             torch.cuda.synchronize()
             if arith == 2:
-                assert ezb.last_path()[0] & 2
+                assert ezb.last_path()[0] & 10
             outs.append(z)
         ezb.set_arith(2)
         rng = float((zin[0].max() - zin[0].min()).item())
