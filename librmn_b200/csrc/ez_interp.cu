@@ -307,32 +307,50 @@ __device__ __forceinline__ float irgd3_w(const F &z, const GridDev &g, float px,
     return (float)nfa(b[0], b2, b3, b4, y, aym, ay0, ayp);
 }
 
-// ez_irgdint_3_wnnc.inc:93-243 ; coefficients on the fly, 4-row strip z(ni, j1:j2), ay4 = ay(j1:j2)
-template <class F>
-__device__ __forceinline__ float irgd3_wnnc(const F &z, const float *__restrict__ ax, const float ay4[4], int ni, int j1, int j2, int wrap,
-                                            float px, float py) {
-    int i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
-    int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
-    int im1, ip1, ip2;
+// ez_irgdint_3_wnnc.inc:93-243 ; coefficients on the fly, 4-row strip z(ni, j1:j2), ay4 = ay(j1:j2).
+// Split into the part that depends on (px, py) only -- computed once per point -- and the part that reads the field,
+// so that callers looping over levels do the fp64 reciprocals once; the arithmetic of each part is unchanged.
+struct WnncPlan {
+    int i, im1, ip1, ip2, j;
+    double cx[6], cy[6];
+    double x, x1, x2, x3, y, y1, y2, y3;
+};
+__device__ __forceinline__ WnncPlan wnnc_plan(const float *__restrict__ ax, const float ay4[4], int ni, int j1, int j2, int wrap, float px, float py) {
+    WnncPlan p;
+    p.i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
+    p.j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
     float fx1 = 0.f, fx2 = 0.f, fx3 = 0.f, fx4 = 0.f;
-    seam_x(wrap, ni, ax, i, true, im1, ip1, ip2, fx1, fx2, fx3, fx4);
-    double x1 = fx1, x2 = fx2, x3 = fx3, x4 = fx4;
-    float ay0 = ay4[j - j1], ayp = ay4[j + 1 - j1];
-    double x = x2 + (x3 - x2) * (double)(px - (float)i);
-    double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
-    double cx[6] = {1.0 / (x2 - x1), 1.0 / (x3 - x1), 1.0 / (x3 - x2), 1.0 / (x4 - x1), 1.0 / (x4 - x2), 1.0 / (x4 - x3)};
-    double y1 = ay4[j - 1 - j1], y2 = ay0, y3 = ayp, y4 = ay4[j + 2 - j1];
+    seam_x(wrap, ni, ax, p.i, true, p.im1, p.ip1, p.ip2, fx1, fx2, fx3, fx4);
+    const double x1 = fx1, x2 = fx2, x3 = fx3, x4 = fx4;
+    const float ay0 = ay4[p.j - j1], ayp = ay4[p.j + 1 - j1];
+    p.x = x2 + (x3 - x2) * (double)(px - (float)p.i);
+    p.y = (double)(ay0 + (ayp - ay0) * (py - (float)p.j));
+    p.cx[0] = 1.0 / (x2 - x1); p.cx[1] = 1.0 / (x3 - x1); p.cx[2] = 1.0 / (x3 - x2);
+    p.cx[3] = 1.0 / (x4 - x1); p.cx[4] = 1.0 / (x4 - x2); p.cx[5] = 1.0 / (x4 - x3);
+    const double y1 = ay4[p.j - 1 - j1], y2 = ay0, y3 = ayp, y4 = ay4[p.j + 2 - j1];
+    p.cy[0] = 1.0 / (y2 - y1); p.cy[1] = 1.0 / (y3 - y1); p.cy[2] = 1.0 / (y3 - y2);
+    p.cy[3] = 1.0 / (y4 - y1); p.cy[4] = 1.0 / (y4 - y2); p.cy[5] = 1.0 / (y4 - y3);
+    p.x1 = x1; p.x2 = x2; p.x3 = x3; p.y1 = y1; p.y2 = y2; p.y3 = y3;
+    return p;
+}
+template <class F>
+__device__ __forceinline__ float wnnc_eval(const WnncPlan &p, const F &z) {
     double b[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        int jj = j - 1 + r;
-        b[r] = newton4<false>(cx, z(im1, jj), z(i, jj), z(ip1, jj), z(ip2, jj), x, x1, x2, x3);
+        int jj = p.j - 1 + r;
+        b[r] = newton4<false>(p.cx, z(p.im1, jj), z(p.i, jj), z(p.ip1, jj), z(p.ip2, jj), p.x, p.x1, p.x2, p.x3);
     }
-    double cy[6] = {1.0 / (y2 - y1), 1.0 / (y3 - y1), 1.0 / (y3 - y2), 1.0 / (y4 - y1), 1.0 / (y4 - y2), 1.0 / (y4 - y3)};
-    double b2 = nfa2(cy[0], b[0], b[1]);
-    double b3 = nfa3(cy[0], cy[1], cy[2], b[0], b[1], b[2]);
-    double b4 = nfa4(cy[0], cy[1], cy[2], cy[3], cy[4], cy[5], b[0], b[1], b[2], b[3]);
-    return (float)nfa(b[0], b2, b3, b4, y, y1, y2, y3);
+    double b2 = nfa2(p.cy[0], b[0], b[1]);
+    double b3 = nfa3(p.cy[0], p.cy[1], p.cy[2], b[0], b[1], b[2]);
+    double b4 = nfa4(p.cy[0], p.cy[1], p.cy[2], p.cy[3], p.cy[4], p.cy[5], b[0], b[1], b[2], b[3]);
+    return (float)nfa(b[0], b2, b3, b4, p.y, p.y1, p.y2, p.y3);
+}
+template <class F>
+__device__ __forceinline__ float irgd3_wnnc(const F &z, const float *__restrict__ ax, const float ay4[4], int ni, int j1, int j2, int wrap,
+                                            float px, float py) {
+    const WnncPlan p = wnnc_plan(ax, ay4, ni, j1, j2, wrap, px, py);
+    return wnnc_eval(p, z);
 }
 
 // c_gdinterp's dispatch (gdinterp.c:133-281) for one point, reference-order arithmetic
@@ -412,6 +430,44 @@ __device__ __noinline__ float polar_point(const FieldFetch &ff, const GridDev &g
     }
     if (degree == EZ_LINEAR) return rgd1(s, g.ni, j1s, j2s, g.ext, px, py);
     return rgd0(s, g.ni, j1s, j2s, px, py);
+}
+
+// The level-invariant half of polar_point for the common heavy case (cubic, irregular 'Z'/'G' source): strip geometry
+// and the wnnc plan.  polar_strip_eval then costs the reference's own newton4 evaluations per level and nothing else.
+struct PolarStrip {
+    int jbase, pole_row, jsrc0;
+    WnncPlan plan;
+};
+__device__ __forceinline__ PolarStrip polar_strip_plan(const GridDev &g, bool north, float px, float py) {
+    PolarStrip ps;
+    float ay4[4];
+    const float *ay = g.ay;
+    if (north) {
+        const int j1s = g.j2 - 2, j2s = j1s + 3;
+        ps.pole_row = 3; ps.jsrc0 = g.j2 - 2; ps.jbase = j1s;
+        if (__ldg(ay + g.j2 - 1) == 90.0f) {
+            ay4[0] = __ldg(ay + g.j2 - 4); ay4[1] = __ldg(ay + g.j2 - 3); ay4[2] = __ldg(ay + g.j2 - 2); ay4[3] = __ldg(ay + g.j2 - 1);
+        } else {
+            ay4[0] = __ldg(ay + g.j2 - 3); ay4[1] = __ldg(ay + g.j2 - 2); ay4[2] = __ldg(ay + g.j2 - 1); ay4[3] = 90.0f;
+        }
+        ps.plan = wnnc_plan(g.ax, ay4, g.ni, j1s, j2s, g.ext, px, py);
+    } else {
+        const int j1s = g.j1 - 1, j2s = j1s + 3;
+        ps.pole_row = 0; ps.jsrc0 = g.j1; ps.jbase = j1s;
+        if (__ldg(ay + g.j1 - 1) == -90.0f) {
+            ay4[0] = __ldg(ay + 0); ay4[1] = __ldg(ay + 1); ay4[2] = __ldg(ay + 2); ay4[3] = __ldg(ay + 3);
+        } else {
+            ay4[0] = -90.0f; ay4[1] = __ldg(ay + 0); ay4[2] = __ldg(ay + 1); ay4[3] = __ldg(ay + 2);
+        }
+        ps.plan = wnnc_plan(g.ax, ay4, g.ni, j1s, j2s, g.ext, px, py);
+    }
+    return ps;
+}
+__device__ __forceinline__ float polar_strip_eval(const PolarStrip &ps, const FieldFetch &ff, float poleval, const float *polerow) {
+    StripFetch s;
+    s.f = ff; s.poleval = poleval; s.polerow = polerow;
+    s.jbase = ps.jbase; s.pole_row = ps.pole_row; s.jsrc0 = ps.jsrc0;
+    return wnnc_eval(ps.plan, s);
 }
 
 // everything ez_corrval.c:54-143 does to one point carrying zone bits

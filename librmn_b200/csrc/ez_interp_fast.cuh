@@ -251,7 +251,7 @@ __device__ __forceinline__ float eval_linear_f32(const PlanLinF &p, const float 
 // 5 linear (fp32 difference form).  Requires plain field access (no hemispheric mirror, no y inversion).
 // The grid descriptor is taken by reference straight from kernel-parameter (constant-bank) space: the Yin/Yang
 // choice is a branch around two instantiations rather than a pointer select, which would force a local copy.
-constexpr int LIST_LCH = 8;   // levels per thread when the kernel runs on the compacted list (blockIdx.y picks the chunk)
+constexpr int LIST_LCH = 4;   // levels per thread when the kernel runs on the compacted list (blockIdx.y picks the chunk)
 
 template <int DEG>
 __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ z, int n, float px, float py,
@@ -287,10 +287,31 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
         return;
     }
     // rare: a point in a polar / outside zone -- reference-order evaluators (ez_corrval semantics)
+    const bool au_n = zbits & ZB_AU_NORD, au_s = zbits & ZB_AU_SUD, pole = zbits & (ZB_POLE_NORD | ZB_POLE_SUD);
+    const bool irr = (g.grtyp == 'Z' || g.grtyp == 'G');
+    // common heavy case: exactly one polar strip, cubic on an irregular source -> strip geometry and fp64 reciprocals once per point
+    if ((au_n != au_s) && !(zbits & ZB_DEHORS) && a.o.degree == EZ_CUBIC && irr && (a.o.vector ? a.polerow != nullptr : true)) {
+        if (!a.o.vector && pole) {   // ez_corrval.c:130-143: the pole lists are written last
+            for (int f = 0; f < nf; f++) zo[f * os] = (zbits & ZB_POLE_SUD) ? a.fs[f0 + f].pole_s : a.fs[f0 + f].pole_n;
+            return;
+        }
+        const PolarStrip ps = polar_strip_plan(g, au_n, px, py);
+        for (int f = 0; f < nf; f++) {
+            const FieldFetch ff = make_fetch(g, z + f * is, a.o.sym_sign);
+            float pv = 0.f;
+            const float *prow = nullptr;
+            if (a.o.vector) prow = a.polerow + (long)(f0 + f) * 2 * g.ni + (au_n ? 0 : g.ni);
+            else pv = au_n ? a.fs[f0 + f].pole_n : a.fs[f0 + f].pole_s;
+            zo[f * os] = polar_strip_eval(ps, ff, pv, prow);
+        }
+        return;
+    }
+    // the interpolated value is only needed when no zone rewrites it
+    const bool need_normal = !(zbits & ZB_DEHORS) && (a.o.vector ? !((au_n || au_s) && a.polerow) : !(au_n || au_s || pole));
     for (int f = 0; f < nf; f++) {
         FieldFetch ff = make_fetch(g, z + f * is, a.o.sym_sign);
         float v = 0.f;
-        if (!(zbits & (ZB_POLE_NORD | ZB_POLE_SUD)) || a.o.vector) v = interp_point(ff, g, a.o.degree, px, py);
+        if (need_normal) v = interp_point(ff, g, a.o.degree, px, py);
         zo[f * os] = zone_point(ff, g, a.o, zbits, a.fs, a.polerow, f0 + f, px, py, v);
     }
 }

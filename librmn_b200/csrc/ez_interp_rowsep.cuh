@@ -156,7 +156,7 @@ __device__ __forceinline__ void rowsep_phase2(const StageRef &zr, int nl, const 
 
 template <int DEG, int P>
 __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArgs &a, const TileDesc &td, int tile, int bx, int by,
-                                               const float *__restrict__ zin, int src_rows, uint32_t smem32, uint32_t vbuf32, uint32_t mbar32) {
+                                               const float *__restrict__ zin, int src_rows, uint32_t smem32, uint32_t vbuf32) {
     constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W, VP = RS_VP;
     const int ni = a.out_ni, nj = a.out_nj;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -224,65 +224,61 @@ __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArg
     constexpr uint32_t VBUF = (uint32_t)(TO * RS_VP) * 16u;
     const int nstages = (nf + LPS - 1) / LPS;
 
-    // ---- the copy side: one 1-D bulk copy (TMA, cp.async.bulk) per box row and level, completion on the slot's mbarrier.
+    // ---- the copy side: 16-byte cp.async (LDGSTS.128), one chunk per thread and level.
     // Level l of a stage sits in its slot with box element (r, j) at float offset delta_l + r P + j, where
-    // delta_l = (float index in memory of source element (r0, c0) of that level) mod 4.  With P == ni (mod 4) the 16-byte
-    // aligned span that covers a source row segment is 16-byte aligned in shared memory for every row, which is what the
-    // bulk copy needs although callers' row lengths are arbitrary.  delta depends on the level only through l = f mod 4
-    // (f = 4 st + l, and 4 st in_stride == 0 mod 4): fixed per slot position.  The span may over-read up to 3 floats on
-    // either side of the segment; it never leaves the 16-byte blocks that hold the segment's first and last element.
-    // Copy t < 4 nrow moves row t % nrow of level t / nrow of each stage.
+    // delta_l = (float index in memory of source element (r0, c0) of that level) mod 4.  With P == ni (mod 4) every
+    // 16-byte aligned chunk of a source row is 16-byte aligned in shared memory for every row of the box, which is what
+    // a 16-byte cp.async needs although callers' row lengths are arbitrary.  delta depends on the level only through
+    // l = f mod 4 (f = 4 st + l, and 4 st in_stride == 0 mod 4): fixed per slot position, so a thread's source and
+    // destination offsets are computed once.  A chunk may over-read up to 3 floats on either side of the row segment;
+    // it never leaves the 16-byte blocks that hold the segment's first and last element.
+    // Thread t copies chunk t % RS_NCK of box row t / RS_NCK (boxes are at most 51 rows tall) of each level.
     const int nrow = min(td.h, src_rows - td.r0);
     const long is = a.in_stride;
     uint32_t sloff[LPS];   // byte offset of box element (0, 0) of level l inside a stage slot
+    int cj = 0;            // packed: byte l = first column of the chunk relative to c0 (-3 .. w + 2), biased by 3
+    unsigned int cvalid = 0u;
+    const int crow = threadIdx.x / RS_NCK, ck4 = 4 * (threadIdx.x - crow * RS_NCK);
     {
         const float *lvl0 = zin + (long)td.r0 * g.ni + td.c0;        // source element (r0, c0) of level 0
 #pragma unroll
-        for (int l = 0; l < LPS; l++) sloff[l] = (uint32_t)l * capB + (uint32_t)((reinterpret_cast<uintptr_t>(lvl0 + l * is) >> 2) & 3u) * 4u;
+        for (int l = 0; l < LPS; l++) {
+            const int dl = (int)((reinterpret_cast<uintptr_t>(lvl0 + l * is) >> 2) & 3u);
+            sloff[l] = (uint32_t)l * capB + (uint32_t)dl * 4u;
+            const int bm = dl + crow * P;            // float offset of box element (crow, 0) in the level's buffer
+            const int m0 = (bm & ~3) + ck4;          // this thread's chunk
+            const int j = m0 - bm;
+            cj |= (j + 3) << (8 * l);
+            if (crow < nrow && j < td.w) cvalid |= 1u << l;
+        }
     }
-    // (the copies are spread over the warps, cq lanes each: a warp issues its bulk copies one lane at a time)
-    const int cq = (LPS * nrow + RS_NCW - 1) / RS_NCW;
-    const int ct = wp * cq + lane;
-    const int cl = ct / nrow, crow = ct - cl * nrow;
-    const bool cactive = lane < cq && cl < LPS;
-    uint32_t cdst = 0, cbytes = 0;
-    const float *csrc = zin;
-    if (cactive) {
-        const float *e0 = zin + (long)cl * is + (long)(td.r0 + crow) * g.ni + td.c0;   // source element (r0 + crow, c0) of level cl
-        const int dl = (int)((reinterpret_cast<uintptr_t>(zin + (long)cl * is + (long)td.r0 * g.ni + td.c0) >> 2) & 3u);
-        const int bm = dl + crow * P;                               // float offset of box element (crow, 0) in the level's buffer
-        const int ms = bm & ~3, me = (bm + td.w + 3) & ~3;          // the aligned span
-        cdst = (uint32_t)(cl * cap + ms) * 4u;
-        cbytes = (uint32_t)(me - ms) * 4u;
-        csrc = e0 + (ms - bm);
-    }
+    const float *csrc = zin + (long)(td.r0 + crow) * g.ni + td.c0 - 3;   // (r0 + crow, c0 - 3) of the next stage to issue
+    const uint32_t cbase = (uint32_t)(crow * P - 3) * 4u;                // byte offset of box element (crow, -3) from element (0, 0)
     auto issue = [&](int st) {   // called with st = 0, 1, 2, ... : csrc walks the levels
-        if (cactive && st < nstages) {
-            const uint32_t slot = (uint32_t)(st % RS_NSTAGE);
-            const uint32_t mb = mbar32 + slot * 8u;
-            if (st * LPS + cl < nf) {
-                mbar_arrive_expect_tx(mb, cbytes);
-                bulk_g2s(smem32 + slot * (LPS * capB) + cdst, csrc, cbytes, mb);
-            } else {
-                mbar_arrive(mb);
+        if (cvalid && st < nstages) {
+            const uint32_t sb = smem32 + (uint32_t)(st % RS_NSTAGE) * (LPS * capB);
+            const float *p = csrc;
+#pragma unroll
+            for (int l = 0; l < LPS; l++) {
+                if (((cvalid >> l) & 1u) && st * LPS + l < nf) {
+                    const uint32_t jb = (uint32_t)(cj >> (8 * l)) & 0xffu;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + sloff[l] + cbase + 4u * jb), "l"(p + jb) : "memory");
+                }
+                p += is;
             }
         }
         csrc += LPS * is;
+        __pipeline_commit();
     };
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < RS_NSTAGE; k++) mbar_init(mbar32 + 8u * k, (uint32_t)(LPS * nrow));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) precedes the bulk copies (async proxy)
-    __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < RS_NSTAGE; k++) issue(k);
+    __pipeline_wait_prior(RS_NSTAGE - 1);   // stage 0 has landed (this thread's share)
+    __syncthreads();                        // ... and everybody else's
 
     char *zo = reinterpret_cast<char *>(a.zout + (long)(by * TO + wp) * ni + oi);
     uint32_t vsel = 0;
-    uint32_t slot = 0, parity = 0;
-    // One CTA barrier per stage: wait for stage st | phase 1 (st) | barrier | refill the slot phase 1 just read | phase 2 (st).
+    uint32_t slot = 0;
+    // One CTA barrier per stage: phase 1 (st) | wait for stage st+1 | barrier | refill the slot phase 1 just read | phase 2 (st).
     // V is double buffered, so phase 2 (st) overlaps other warps' phase 1 (st+1).
 #pragma unroll 1
     for (int st = 0; st < nstages; st++) {
@@ -290,17 +286,17 @@ __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArg
         const uint32_t sl[4] = {sbase + sloff[0], sbase + sloff[1], sbase + sloff[2], sbase + sloff[3]};
         const int nl = nf - st * LPS;
         const uint32_t vld[2] = {vld0[0] + vsel, vld0[1] + vsel};
-        mbar_wait(mbar32 + slot * 8u, parity);
         StageRef zr;
         if (nl >= LPS) zr = rowsep_phase1<DEG, P, true>(sl, LPS, p1off, vst0 + vsel, td.w, lane, wya);
         else zr = rowsep_phase1<DEG, P, false>(sl, nl, p1off, vst0 + vsel, td.w, lane, wya);
+        __pipeline_wait_prior(RS_NSTAGE - 2);
         __syncthreads();
         issue(st + RS_NSTAGE);
         if (nl >= LPS) rowsep_phase2<DEG, true>(zr, LPS, vld, wxa, sm1, okmask, zo, osB, rstepB);
         else rowsep_phase2<DEG, false>(zr, nl, vld, wxa, sm1, okmask, zo, osB, rstepB);
         vsel ^= VBUF;
         zo += LPS * osB;
-        if (++slot == RS_NSTAGE) { slot = 0; parity ^= 1u; }
+        if (++slot == RS_NSTAGE) slot = 0;
     }
 }
 
@@ -316,9 +312,8 @@ __global__ void __launch_bounds__(RS_NTHR, EZ_ROWSEP_MINB) k_interp_rowsep(const
     __syncthreads();
     const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t vbuf32 = smem32 + (uint32_t)nstage_floats * 4u;
-    const uint32_t mbar32 = vbuf32 + 2u * (uint32_t)(TO * RS_VP) * 16u;
-    if (td.panel) rowsep_compute<DEG, P>(a.src2, a, td, tile, blockIdx.x, by, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32, vbuf32, mbar32);
-    else rowsep_compute<DEG, P>(a.src, a, td, tile, blockIdx.x, by, a.zin, a.src.j2 - a.src.j1 + 1, smem32, vbuf32, mbar32);
+    if (td.panel) rowsep_compute<DEG, P>(a.src2, a, td, tile, blockIdx.x, by, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32, vbuf32);
+    else rowsep_compute<DEG, P>(a.src, a, td, tile, blockIdx.x, by, a.zin, a.src.j2 - a.src.j1 + 1, smem32, vbuf32);
 }
 
 }  // namespace

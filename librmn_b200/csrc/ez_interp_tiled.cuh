@@ -35,6 +35,10 @@ constexpr int TO = 2 * TT;         // target points per tile side
 #ifndef EZ_TILED_MINB
 #define EZ_TILED_MINB 3
 #endif
+#ifndef EZ_TILED_UNROLL
+#define EZ_TILED_UNROLL 1
+#endif
+constexpr int TILED_UNROLL = EZ_TILED_UNROLL;   // levels of a stage evaluated per loop iteration in the window kernel
 constexpr int TILE_CAP = EZ_TILE_CAP;     // floats per shared-memory buffer
 constexpr int LPS = EZ_LPS;               // source levels per pipeline stage (one CTA barrier per stage)
 constexpr int NSTAGE = EZ_NSTAGE;          // buffers per CTA: the producer warp runs NSTAGE-1 source levels ahead of the compute warps
@@ -360,7 +364,7 @@ __device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs
         const float *sbase = smem + (st % NSTAGE) * LPS * cap + base;
         const int nl = min(LPS, nf - st * LPS);
         if (fast) {
-#pragma unroll 1
+#pragma unroll TILED_UNROLL
             for (int l = 0; l < nl; l++) {
                 const float *s = sbase + l * cap;
                 const float zc = s[(W / 2) * pitch + W / 2];
