@@ -1422,15 +1422,7 @@ int xysint_dev(Grid &g, float *d_zout, const float *d_zin, const float *d_x, con
         a.src = to_dev(g);
     }
     S.last_path = 1;
-    if (a.tiles && a.nlist > 0 && !S.s_aux) {
-        if (cudaStreamCreateWithFlags(&S.s_aux, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming) != cudaSuccess) {
-            S.s_aux = nullptr;   // fall back to the single-stream order
-            (void)cudaGetLastError();
-        }
-    }
-    S.launches += ezk::interp(a, S.stream, S.s_aux, S.ev_fork, S.ev_join);
+    S.launches += ezk::interp(a, S.stream);
     return 0;
 }
 
