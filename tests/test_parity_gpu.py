@@ -434,3 +434,69 @@ def test_full_size_linearity_and_constants(ezb, cuda_ok):
     x, y, zb, counts = ezb.get_gridset(c.gdout, c.gdin, c.n_out)
     yang = int(counts[5])
     assert 0.55 < yang / c.n_out < 0.70      # Yin's 270 x 90 degree core covers 37.5 % of an equal-angle lat-lon grid
+
+
+# ---------------------------------------------------------------------------------------------------
+# the row-separable tile kernel (ez_interp_rowsep.cuh): lat-lon targets fed from aligned sources
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("degree", ["linear", "cubic"])
+def test_rowsep_kernel_taken_and_matches_oracle(ezb, ezref, cuda_ok, degree):
+    """C5 (every tile) and C2 (the Yin tiles) must take the row-separable kernel and stay within tolerance of the oracle."""
+    ezb.set_arith(2)
+    for mk in (lambda L: configs.c5(L, res_src=0.6, res_dst=0.4, degree=degree), lambda L: configs.c2(L, res_src=0.6, res_dst=0.4, degree=degree)):
+        c_b, c_r = mk(ezb), mk(ezref)
+        rc_b, out_b = cases.run_case(ezb, c_b)
+        path, nlist = ezb.last_path()
+        assert path & 8, "%s did not take the row-separable kernel (path=%d)" % (c_b.name, path)
+        rc_r, out_r = cases.run_case(ezref, c_r)
+        assert rc_b == rc_r
+        rng = cases.field_range(c_b)
+        err = float(np.abs(out_b.astype(np.float64) - out_r).max()) / rng
+        assert err < TOL, "%s: %g of range" % (c_b.name, err)
+
+
+@pytest.mark.parametrize("degree", ["linear", "cubic"])
+def test_rowsep_levels_alignment_and_offsets(ezb, cuda_ok, degree):
+    """Row-separable kernel against the fp64 weight-form per-point kernel (arith = 1) on the same gridset:
+    every level count around the 4-level stage (tail stages of 1..3 levels), source arrays that start at each of the
+    four 16-byte phases (the congruent-pitch staging must absorb them), row lengths of every residue mod 4, a field
+    with a large offset (the difference form keeps the error relative to the RANGE), a missing-value marker in a
+    corner of the field (reference value falls back to 0 there)."""
+    import torch
+    for ni_src in (360, 361, 362, 363):
+        gdin = configs.def_L(ezb, ni_src, 181, -90.0, 0.0, 1.0, 360.0 / ni_src)
+        gdout = configs.def_L(ezb, 300, 150, -60.0, 10.0, 0.7, 0.9)
+        c = configs.Case("rowsep", ezb)
+        c.opts = {"interp_degree": degree}
+        c.apply_options()
+        assert ezb.ezdefset(gdout, gdin) == 1
+        lat, lon = np.meshgrid(np.arange(181) - 90.0, np.arange(ni_src) * (360.0 / ni_src), indexing="ij")
+        base = configs.field(lat, lon, k=1).astype(np.float32)
+        for nf, shift, offset, marker in ((1, 0, 0.0, False), (2, 1, 0.0, False), (3, 2, 0.0, False), (5, 3, 0.0, False), (9, 1, 1.0e5, False),
+                                          (6, 0, 0.0, True)):
+            fields = np.stack([base + 0.37 * k + offset for k in range(nf)]).astype(np.float32)
+            if marker:
+                fields[:, 0, 0] = 1.0e30      # never inside a target stencil here (targets start at lat -60), but it is a tile's zref candidate
+                fields[:, 40, 12] = 1.0e30    # this one is inside stencils: both kernels must agree on the garbage's neighbours
+            buf = torch.zeros(fields.size + 8, dtype=torch.float32, device="cuda")
+            zin = buf[shift:shift + fields.size].view(nf, 181, ni_src)
+            zin.copy_(torch.from_numpy(fields))
+            outs = []
+            for arith in (2, 1):
+                ezb.set_arith(arith)
+                z = torch.full((nf, 150, 300), -1.0, device="cuda", dtype=torch.float32)
+                assert ezb.ezsint_batch(z, zin, nf) >= 0
+                torch.cuda.synchronize()
+                if arith == 2:
+                    assert ezb.last_path()[0] & 8, "row-separable kernel not taken (ni=%d)" % ni_src
+                outs.append(z.double())
+            ezb.set_arith(2)
+            rng = float(base.max() - base.min())
+            d = (outs[0] - outs[1]).abs()
+            if marker:
+                ok = outs[1].abs() < 1e20            # away from the marker's stencils
+                assert ok.float().mean().item() > 0.99
+                d = d[ok]
+            # (a tile whose reference cell holds the marker falls back to the plain fp32 weight form: error ~1e-6 of the MAGNITUDE)
+            ulp_out = float(np.spacing(np.float32(np.abs(fields[np.abs(fields) < 1e20]).max())))   # the outputs are fp32: two correct roundings may differ by one ulp
+            assert d.max().item() < (2e-5 if marker else 3e-6) * rng + ulp_out, (ni_src, nf, shift, offset, marker, d.max().item() / rng)
