@@ -160,8 +160,9 @@ def main():
             return 0
         steps = max(1, min(args.steps, 5))
         warm = max(1, min(args.warmup, 2))
-        v, ms, case, desc = cpu_reference_run(args.workload, args.cpu_sample_levels, cores, steps, warm)
-        sample = "%d of the workload's levels per step, %d threads each calling c_ezdefset+c_ezsint on its own levels" % (args.cpu_sample_levels, cores)
+        nsample = max(args.cpu_sample_levels, cores)   # at least one level per host thread, so that every core has work
+        v, ms, case, desc = cpu_reference_run(args.workload, nsample, cores, steps, warm)
+        sample = "%d of the workload's levels per step, %d threads each calling c_ezdefset+c_ezsint on its own levels" % (nsample, cores)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-on-f32", "data": "synthetic",
                 "config": {"workload": desc, "sample": sample},
@@ -250,6 +251,17 @@ def main():
     barrier()
     launches = B.launch_count()
     path, nlist = B.last_path()
+    # per-kernel durations of the same step, measured live with CUDA events recorded by the library on the launching
+    # stream around each kernel (c_ezb200_set_timing): a few extra steps outside the K timed ones
+    B.set_timing(True)
+    kms = []
+    for _ in range(5):
+        step_dev()
+        ms3, tiles3 = B.last_kernel_ms()
+        if ms3:
+            kms.append(ms3)
+    B.set_timing(False)
+    torch.cuda.synchronize()
     total_ms = e_all0.elapsed_time(e_all1)
     step_ms = [a.elapsed_time(b) for a, b in evs]
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -289,29 +301,57 @@ def main():
 
     peak, peak_kind = measured_peak()
     abytes = algorithmic_bytes(case, nlev)
-    kern_ms = statistics.mean(step_ms)   # one step == one launch of the dominant kernel (+ its launch gap)
-    achieved = abytes / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_kind": peak_kind, "kernel": ("k_interp_tiled<%s>" if path & 2 else "k_interp_fast<%s>") % {"nearest": 0, "linear": 1, "cubic": 3}[case.opts.get("interp_degree", "cubic")],
-                "points_on_per_point_list": nlist,
-                "algorithmic_bytes_per_launch": abytes, "kernel_ms": kern_ms}
+    step_kern_ms = statistics.mean(step_ms)   # every kernel of one step (tile kernels + list kernel + pre-pass)
+    deg = {"nearest": 0, "linear": 1, "cubic": 3}[case.opts.get("interp_degree", "cubic")]
+    kernels = None
+    if kms and (path & 10):
+        # The step's work is split by target tile between the two tile kernels (plus the short per-point list).  The
+        # dominant kernel is the one with the larger measured duration; its algorithmic bytes are the step's bytes times
+        # its share of the target points (every tile reads its own source box and the gridset once per batch).
+        rs_ms, win_ms, list_ms = [statistics.median(k[i] for k in kms) for i in range(3)]
+        t_rs, t_win, n_list = tiles3
+        tile_pts = max(1, nout - n_list)
+        share = {"rowsep": tile_pts * (t_rs / max(1, t_rs + t_win)) / nout, "window": tile_pts * (t_win / max(1, t_rs + t_win)) / nout}
+        kernels = {"k_interp_rowsep<%d>" % deg: {"ms": rs_ms, "tiles": t_rs, "points_share": share["rowsep"]},
+                   "k_interp_tiled<%d>" % deg: {"ms": win_ms, "tiles": t_win, "points_share": share["window"]},
+                   "k_interp_fast (list)": {"ms": list_ms, "points": n_list}}
+        if rs_ms >= win_ms:
+            dom, dom_ms, dom_share = "k_interp_rowsep<%d>" % deg, rs_ms, share["rowsep"]
+        else:
+            dom, dom_ms, dom_share = "k_interp_tiled<%d>" % deg, win_ms, share["window"]
+        dom_bytes = abytes * dom_share
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_kind": peak_kind, "kernel": dom, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
+                    "kernels": kernels,
+                    "step": {"algorithmic_bytes": abytes, "ms": step_kern_ms, "achieved": abytes / (step_kern_ms * 1e-3) / 1e9,
+                             "frac": abytes / (step_kern_ms * 1e-3) / 1e9 / peak},
+                    "points_on_per_point_list": nlist}
+    else:
+        achieved = abytes / (step_kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_kind": peak_kind, "kernel": "k_interp_fast<%d>" % deg, "kernel_ms": step_kern_ms,
+                    "algorithmic_bytes_per_launch": abytes, "points_on_per_point_list": nlist}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
-            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        roofline["traffic"] = tj.get("kernels", {}).get(roofline["kernel"], {}).get("dram_bytes_per_launch", tj.get("dram_bytes_per_launch"))
+        roofline["traffic_source"] = tj.get("source")
 
     cpu_baseline = None
     if not args.no_cpu_baseline and os.path.exists(REF_SO):
         try:
-            v, ms, _, _ = cpu_reference_run(args.workload, min(args.cpu_sample_levels, nlev), cores, 2, 1)
+            nsample = min(max(args.cpu_sample_levels, cores), max(nlev, 1))   # at least one level per host thread where the workload has them
+            v, ms, _, _ = cpu_reference_run(args.workload, nsample, cores, 2, 1)
             cpu_baseline = {"value": v, "unit": unit, "cores": cores, "kind": "reference",
                             "sample": "%d levels of the same workload, %d host threads (one c_ezdefset+c_ezsint stream per thread), %.0f ms/step" % (
-                                min(args.cpu_sample_levels, nlev), cores, ms)}
+                                nsample, cores, ms)}
         except Exception as ex:   # the baseline is reported, never required for the GPU number
             cpu_baseline = {"value": None, "unit": unit, "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64-on-f32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.arith == 2 else "f64",
             "data": "synthetic",
             "config": {"workload": desc, "levels_per_gpu": nlev, "n_src": nin, "n_out": nout, "arith": args.arith,
                        "l2": "inputs larger than L2 (%.0f MB in + %.0f MB out per step)" % (comps * nlev * nin * 4 / 1e6, comps * nlev * nout * 4 / 1e6),

@@ -132,10 +132,17 @@ int32_t c_ezb200_get_arith(void);
 int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, uint8_t *zonebits, int32_t *counts);
 /* number of CUDA kernels launched by the calling thread since the last call with reset != 0 */
 int64_t c_ezb200_launch_count(int32_t reset);
-/* kernels used by the calling thread's last interpolation launch: bit 0 per-point kernel, bit 1 tiled kernel,
-   bit 2 per-point kernel on the compacted list of points the tiles leave out (*nlist = its length) */
+/* kernels used by the calling thread's last interpolation launch: bit 0 per-point kernel, bit 1 window tile kernel,
+   bit 2 per-point kernel on the compacted list of points the tiles leave out (*nlist = its length),
+   bit 3 row-separable tile kernel */
 int32_t c_ezb200_last_path(int32_t *nlist);
 /* block until the calling thread's stream is idle ; returns 0 or -1 with the CUDA error on stderr */
+/* Measurement aid: with timing on, every tiled interpolation launch records CUDA events on the session stream around its
+ * kernels; c_ezb200_last_kernel_ms returns ms[3] = {row-separable tile kernel, window tile kernel, per-point list kernel}
+ * of the LAST launch and tiles[3] = {tiles on the row-separable kernel, tiles on the window kernel, points on the list}.
+ * Returns -1 when the last launch was not timed. */
+int32_t c_ezb200_set_timing(int32_t on);
+int32_t c_ezb200_last_kernel_ms(float *ms, int32_t *tiles);
 int32_t c_ezb200_sync(void);
 const char *c_ezb200_version(void);
 

@@ -99,6 +99,8 @@ class EzLib:
             L.c_ezb200_launch_count.restype = C.c_int64
             L.c_ezb200_version.restype = C.c_char_p
             L.c_ezb200_last_path.argtypes = [C.POINTER(_i32)]
+            L.c_ezb200_set_timing.argtypes = [_i32]
+            L.c_ezb200_last_kernel_ms.argtypes = [C.POINTER(C.c_float), C.POINTER(_i32)]
 
     # ---- descriptors -------------------------------------------------------------------------
     def cxgaig(self, grtyp, xg1, xg2, xg3, xg4):
@@ -275,9 +277,20 @@ class EzLib:
         return self.lib.c_ezb200_launch_count(1 if reset else 0)
 
     def last_path(self):
-        """(bitmask, nlist) of the kernels the last interpolation launch used: 1 per-point, 2 tiled, 4 per-point on the compacted list."""
+        """(bitmask, nlist) of the kernels the last interpolation launch used: 1 per-point, 2 window tile kernel, 4 per-point on
+        the compacted list, 8 row-separable tile kernel."""
         n = _i32(0)
         return self.lib.c_ezb200_last_path(C.byref(n)), n.value
+
+    def set_timing(self, on=True):
+        return self.lib.c_ezb200_set_timing(1 if on else 0)
+
+    def last_kernel_ms(self):
+        """((rowsep_ms, window_ms, list_ms) or None, (tiles_rowsep, tiles_window, list_points)) of the last tiled launch."""
+        ms = (C.c_float * 3)()
+        tiles = (_i32 * 3)()
+        rc = self.lib.c_ezb200_last_kernel_ms(ms, tiles)
+        return (tuple(ms) if rc == 0 else None), tuple(tiles)
 
     def sync(self):
         return self.lib.c_ezb200_sync()

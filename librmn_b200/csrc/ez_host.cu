@@ -111,6 +111,10 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     cudaStream_t stream = 0;
     int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
+    bool timing = false;        // c_ezb200_set_timing: record events around the tile kernels of each interpolation launch
+    bool timing_valid = false;
+    ezk::InterpTiming tev = {{nullptr, nullptr, nullptr, nullptr}};
+    int last_tiles[3] = {0, 0, 0};   // tiles on the row-separable kernel, on the window kernel, active tiles
     int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 window tile kernel, 4 per-point on the compacted list, 8 row-separable tile kernel
     int last_nlist = 0;
     DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4];
@@ -822,7 +826,12 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     }
     S.last_path = a.tiles ? ((a.ntiles_window > 0 ? 2 : 0) | (a.nlist > 0 ? 4 : 0) | (a.ntiles_rowsep > 0 ? 8 : 0)) : 1;
     S.last_nlist = a.tiles ? a.nlist : 0;
-    S.launches += ezk::interp(a, S.stream);
+    S.last_tiles[0] = a.tiles ? a.ntiles_rowsep : 0;
+    S.last_tiles[1] = a.tiles ? a.ntiles_window : 0;
+    S.last_tiles[2] = S.last_tiles[0] + S.last_tiles[1];
+    const bool timed = S.timing && a.tiles && S.tev.ev[0];
+    S.timing_valid = timed;
+    S.launches += ezk::interp(a, S.stream, timed ? &S.tev : nullptr);
     // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged
     if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
         ezk::corrbgd(d_zout, out_stride, nfields, out.ni, out.nj, out.ig[0], S.stream);
@@ -1136,6 +1145,22 @@ int64_t c_ezb200_launch_count(int32_t reset) {
 int32_t c_ezb200_last_path(int32_t *nlist) {
     if (nlist) *nlist = S.last_nlist;
     return S.last_path;
+}
+int32_t c_ezb200_set_timing(int32_t on) {
+    S.timing = on != 0;
+    S.timing_valid = false;
+    if (S.timing && !S.tev.ev[0])
+        for (int k = 0; k < 4; k++) CUDA_OK(cudaEventCreate(&S.tev.ev[k]));
+    return 0;
+}
+int32_t c_ezb200_last_kernel_ms(float *ms, int32_t *tiles) {
+    if (tiles) { tiles[0] = S.last_tiles[0]; tiles[1] = S.last_tiles[1]; tiles[2] = S.last_nlist; }
+    if (!ms) return 0;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (!S.timing_valid) return -1;
+    CUDA_OK(cudaEventSynchronize(S.tev.ev[3]));
+    for (int k = 0; k < 3; k++) CUDA_OK(cudaEventElapsedTime(&ms[k], S.tev.ev[k], S.tev.ev[k + 1]));
+    return 0;
 }
 int32_t c_ezb200_sync(void) {
     CUDA_OK(cudaStreamSynchronize(S.stream));

@@ -469,7 +469,6 @@ __device__ __forceinline__ float polar_strip_eval(const PolarStrip &ps, const Fi
     s.jbase = ps.jbase; s.pole_row = ps.pole_row; s.jsrc0 = ps.jsrc0;
     return wnnc_eval(ps.plan, s);
 }
-
 // everything ez_corrval.c:54-143 does to one point carrying zone bits
 __device__ __noinline__ float zone_point(const FieldFetch &ff, const GridDev &g, const InterpOpts &o, uint8_t bits, const FieldScalars *fs,
                                          const float *prow, int f, float px, float py, float normal) {
@@ -711,7 +710,7 @@ void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned i
     k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor);
 }
 
-int interp(const InterpArgs &a, cudaStream_t s) {
+int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
     if (a.tiles) {
         // tiled path: the two tile kernels for every point that fits, the per-point kernel for the compacted rest
@@ -737,6 +736,7 @@ int interp(const InterpArgs &a, cudaStream_t s) {
 #undef EZ_RS_ATTR
             attr_set = true;
         }
+        if (timing) cudaEventRecord(timing->ev[0], s);
         if (a.ntiles_rowsep > 0) {
             const bool cub = a.o.degree == EZ_CUBIC;
 #define EZ_RS_LAUNCH(P)                                                               \
@@ -748,11 +748,13 @@ int interp(const InterpArgs &a, cudaStream_t s) {
 #undef EZ_RS_LAUNCH
             launches++;
         }
+        if (timing) cudaEventRecord(timing->ev[1], s);
         if (a.ntiles_window > 0) {
             if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
             else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
             launches++;
         }
+        if (timing) cudaEventRecord(timing->ev[2], s);
         if (a.nlist > 0) {
             InterpArgs b = a;
             b.tiles = nullptr;
@@ -760,6 +762,7 @@ int interp(const InterpArgs &a, cudaStream_t s) {
             launch_fast(b, s);
             launches++;
         }
+        if (timing) cudaEventRecord(timing->ev[3], s);
         return launches;
     }
     if (a.o.arith >= 1 && launch_fast(a, s)) return 1;

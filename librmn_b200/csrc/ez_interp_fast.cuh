@@ -107,6 +107,39 @@ __device__ __forceinline__ void newton_weights(const double c[6], double t1, dou
     w[3] = P3 * (c[3] * c[4] * c[5]);
 }
 
+// Weight form of the same interpolant (the Newton basis expanded in the samples, fp64): 16 samples, 20 DFMA per level
+// instead of five Newton evaluations.  Differs from the reference's evaluation order at the 1e-16 level.
+struct PolarStripW {
+    int jbase, pole_row, jsrc0;
+    int i, im1, ip1, ip2, j;
+    double wx[4], wy[4];
+};
+__device__ __forceinline__ PolarStripW polar_strip_weights(const PolarStrip &ps) {
+    PolarStripW w;
+    w.jbase = ps.jbase; w.pole_row = ps.pole_row; w.jsrc0 = ps.jsrc0;
+    const WnncPlan &p = ps.plan;
+    w.i = p.i; w.im1 = p.im1; w.ip1 = p.ip1; w.ip2 = p.ip2; w.j = p.j;
+    newton_weights(p.cx, p.x - p.x1, p.x - p.x2, p.x - p.x3, w.wx);
+    newton_weights(p.cy, p.y - p.y1, p.y - p.y2, p.y - p.y3, w.wy);
+    return w;
+}
+__device__ __forceinline__ float polar_strip_eval_w(const PolarStripW &w, const FieldFetch &ff, float poleval, const float *polerow) {
+    StripFetch s;
+    s.f = ff; s.poleval = poleval; s.polerow = polerow;
+    s.jbase = w.jbase; s.pole_row = w.pole_row; s.jsrc0 = w.jsrc0;
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int jj = w.j - 1 + r;
+        double t = w.wx[0] * (double)s(w.im1, jj);
+        t = fma(w.wx[1], (double)s(w.i, jj), t);
+        t = fma(w.wx[2], (double)s(w.ip1, jj), t);
+        t = fma(w.wx[3], (double)s(w.ip2, jj), t);
+        acc = fma(w.wy[r], t, acc);
+    }
+    return (float)acc;
+}
+
 // cubic8.cdk:3 expanded in the samples (fp32-rounded literals kept)
 __device__ __forceinline__ void cubic_weights(double d, double w[4]) {
     const double c6 = (double)0.1666666666666f, c3 = (double)0.3333333333333f, h = 0.5;
@@ -251,7 +284,10 @@ __device__ __forceinline__ float eval_linear_f32(const PlanLinF &p, const float 
 // 5 linear (fp32 difference form).  Requires plain field access (no hemispheric mirror, no y inversion).
 // The grid descriptor is taken by reference straight from kernel-parameter (constant-bank) space: the Yin/Yang
 // choice is a branch around two instantiations rather than a pointer select, which would force a local copy.
-constexpr int LIST_LCH = 4;   // levels per thread when the kernel runs on the compacted list (blockIdx.y picks the chunk)
+#ifndef EZ_LIST_LCH
+#define EZ_LIST_LCH 16
+#endif
+constexpr int LIST_LCH = EZ_LIST_LCH;   // levels per thread when the kernel runs on the compacted list (blockIdx.y picks the chunk)
 
 template <int DEG>
 __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ z, int n, float px, float py,
@@ -293,6 +329,18 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
     if ((au_n != au_s) && !(zbits & ZB_DEHORS) && a.o.degree == EZ_CUBIC && irr && (a.o.vector ? a.polerow != nullptr : true)) {
         if (!a.o.vector && pole) {   // ez_corrval.c:130-143: the pole lists are written last
             for (int f = 0; f < nf; f++) zo[f * os] = (zbits & ZB_POLE_SUD) ? a.fs[f0 + f].pole_s : a.fs[f0 + f].pole_n;
+            return;
+        }
+        if (a.o.arith >= 1) {   // weight form (arith 0 keeps the reference's evaluation order)
+            const PolarStripW pw = polar_strip_weights(polar_strip_plan(g, au_n, px, py));
+            for (int f = 0; f < nf; f++) {
+                const FieldFetch ff = make_fetch(g, z + f * is, a.o.sym_sign);
+                float pv = 0.f;
+                const float *prow = nullptr;
+                if (a.o.vector) prow = a.polerow + (long)(f0 + f) * 2 * g.ni + (au_n ? 0 : g.ni);
+                else pv = au_n ? a.fs[f0 + f].pole_n : a.fs[f0 + f].pole_s;
+                zo[f * os] = polar_strip_eval_w(pw, ff, pv, prow);
+            }
             return;
         }
         const PolarStrip ps = polar_strip_plan(g, au_n, px, py);

@@ -79,7 +79,11 @@ void split_u(const float *y, int njyin, float *ty, uint8_t *zb, int npts, cudaSt
 // K10 pre-pass: per-field pole-row means (sequential fp32 sums, bit-faithful to ez_calcpoleval) and min/max.
 void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s);
 // K0-K9: the gather-interpolation kernel.  Returns the number of kernel launches issued.
-int interp(const InterpArgs &a, cudaStream_t s);
+// optional per-kernel timing of the tiled path: events recorded on `s` around [row-separable | window | list] launches
+struct InterpTiming {
+    cudaEvent_t ev[4];   // before row-separable, before window, before list, after list
+};
+int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing = nullptr);
 // tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry
 bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
