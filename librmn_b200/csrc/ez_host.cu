@@ -114,6 +114,8 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     bool timing = false;        // c_ezb200_set_timing: record events around the tile kernels of each interpolation launch
     bool timing_valid = false;
     ezk::InterpTiming tev = {{nullptr, nullptr, nullptr, nullptr}};
+    ezk::InterpFork fork = {{nullptr, nullptr}, nullptr, {nullptr, nullptr}};   // created on the first tiled launch
+    bool fork_ok = false, fork_tried = false;
     int last_tiles[3] = {0, 0, 0};   // tiles on the row-separable kernel, on the window kernel, active tiles
     int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 window tile kernel, 4 per-point on the compacted list, 8 row-separable tile kernel
     int last_nlist = 0;
@@ -831,7 +833,17 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     S.last_tiles[2] = S.last_tiles[0] + S.last_tiles[1];
     const bool timed = S.timing && a.tiles && S.tev.ev[0];
     S.timing_valid = timed;
-    S.launches += ezk::interp(a, S.stream, timed ? &S.tev : nullptr);
+    if (a.tiles && !S.fork_tried) {
+        S.fork_tried = true;
+        static const bool conc_on = !(getenv("EZB200_CONCURRENT") && atoi(getenv("EZB200_CONCURRENT")) == 0);
+        S.fork_ok = conc_on && cudaStreamCreateWithFlags(&S.fork.aux[0], cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&S.fork.aux[1], cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&S.fork.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&S.fork.ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&S.fork.ev_join[1], cudaEventDisableTiming) == cudaSuccess;
+        if (!S.fork_ok) (void)cudaGetLastError();
+    }
+    S.launches += ezk::interp(a, S.stream, timed ? &S.tev : nullptr, S.fork_ok ? &S.fork : nullptr);
     // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged
     if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
         ezk::corrbgd(d_zout, out_stride, nfields, out.ni, out.nj, out.ig[0], S.stream);

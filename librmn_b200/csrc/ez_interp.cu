@@ -710,7 +710,7 @@ void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned i
     k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor);
 }
 
-int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing) {
+int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, const InterpFork *fork) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
     if (a.tiles) {
         // tiled path: the two tile kernels for every point that fits, the per-point kernel for the compacted rest
@@ -736,20 +736,35 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing) {
 #undef EZ_RS_ATTR
             attr_set = true;
         }
+        // Concurrent mode (no per-kernel timing): the window kernel, the row-separable kernel and the list kernel write
+        // disjoint target points; with two or more of them they go to separate streams between a fork and a join event.
+        const int nk = (a.ntiles_rowsep > 0) + (a.ntiles_window > 0) + (a.nlist > 0);
+        const bool conc = fork && !timing && nk >= 2;
+        cudaStream_t s_rs = s, s_list = s;
+        if (conc) {
+            cudaEventRecord(fork->ev_fork, s);
+            if (a.ntiles_window > 0 && a.ntiles_rowsep > 0) { s_rs = fork->aux[0]; cudaStreamWaitEvent(s_rs, fork->ev_fork, 0); }
+            if (a.nlist > 0) { s_list = fork->aux[1]; cudaStreamWaitEvent(s_list, fork->ev_fork, 0); }
+        }
         if (timing) cudaEventRecord(timing->ev[0], s);
+        if (a.ntiles_window > 0 && conc) {   // the largest kernel first
+            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
+            else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
+            launches++;
+        }
         if (a.ntiles_rowsep > 0) {
             const bool cub = a.o.degree == EZ_CUBIC;
 #define EZ_RS_LAUNCH(P)                                                               \
     case P:                                                                           \
-        if (cub) k_interp_rowsep<3, P><<<grid, RS_NTHR, smem_rs, s>>>(ar);   \
-        else k_interp_rowsep<1, P><<<grid, RS_NTHR, smem_rs, s>>>(ar);       \
+        if (cub) k_interp_rowsep<3, P><<<grid, RS_NTHR, smem_rs, s_rs>>>(ar);   \
+        else k_interp_rowsep<1, P><<<grid, RS_NTHR, smem_rs, s_rs>>>(ar);       \
         break;
             switch (rs_p) { EZ_RS_LAUNCH(35) EZ_RS_LAUNCH(36) EZ_RS_LAUNCH(37) EZ_RS_LAUNCH(38) }
 #undef EZ_RS_LAUNCH
             launches++;
         }
         if (timing) cudaEventRecord(timing->ev[1], s);
-        if (a.ntiles_window > 0) {
+        if (a.ntiles_window > 0 && !conc) {
             if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
             else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
             launches++;
@@ -759,8 +774,12 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing) {
             InterpArgs b = a;
             b.tiles = nullptr;
             b.tile_flags = nullptr;
-            launch_fast(b, s);
+            launch_fast(b, s_list);
             launches++;
+        }
+        if (conc) {
+            if (s_rs != s) { cudaEventRecord(fork->ev_join[0], s_rs); cudaStreamWaitEvent(s, fork->ev_join[0], 0); }
+            if (s_list != s) { cudaEventRecord(fork->ev_join[1], s_list); cudaStreamWaitEvent(s, fork->ev_join[1], 0); }
         }
         if (timing) cudaEventRecord(timing->ev[3], s);
         return launches;

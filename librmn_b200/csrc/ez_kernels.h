@@ -83,7 +83,13 @@ void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldSc
 struct InterpTiming {
     cudaEvent_t ev[4];   // before row-separable, before window, before list, after list
 };
-int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing = nullptr);
+// optional fork/join resources: the kernels of one tiled launch touch disjoint target points, so they may run concurrently
+// (the smaller kernels fill the SMs the largest one leaves idle in its last wave)
+struct InterpFork {
+    cudaStream_t aux[2];
+    cudaEvent_t ev_fork, ev_join[2];
+};
+int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing = nullptr, const InterpFork *fork = nullptr);
 // tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry
 bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
