@@ -748,8 +748,8 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         }
         if (timing) cudaEventRecord(timing->ev[0], s);
         if (a.ntiles_window > 0 && conc) {   // the largest kernel first
-            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
-            else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
+            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_WIN, smem, s>>>(a);
+            else k_interp_tiled<1><<<grid, NTHR_WIN, smem, s>>>(a);
             launches++;
         }
         if (a.ntiles_rowsep > 0) {
@@ -765,8 +765,8 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         }
         if (timing) cudaEventRecord(timing->ev[1], s);
         if (a.ntiles_window > 0 && !conc) {
-            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_TILED, smem, s>>>(a);
-            else k_interp_tiled<1><<<grid, NTHR_TILED, smem, s>>>(a);
+            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_WIN, smem, s>>>(a);
+            else k_interp_tiled<1><<<grid, NTHR_WIN, smem, s>>>(a);
             launches++;
         }
         if (timing) cudaEventRecord(timing->ev[2], s);

@@ -33,12 +33,20 @@ constexpr int TO = 2 * TT;         // target points per tile side
 #define EZ_LPS 4
 #endif
 #ifndef EZ_TILED_MINB
-#define EZ_TILED_MINB 3
+#define EZ_TILED_MINB 2
 #endif
 #ifndef EZ_TILED_UNROLL
 #define EZ_TILED_UNROLL 1
 #endif
-constexpr int TILED_UNROLL = EZ_TILED_UNROLL;   // levels of a stage evaluated per loop iteration in the window kernel
+constexpr int TILED_UNROLL = EZ_TILED_UNROLL;
+#ifndef EZ_TILED_NOPROD
+#define EZ_TILED_NOPROD 1
+#endif
+// EZ_TILED_NOPROD: the window kernel stages with 16-byte cp.async issued by all its threads through a staging pitch
+// congruent to the source row length mod 4 (see ez_interp_rowsep.cuh), no producer warp, one barrier per stage.
+constexpr bool TILED_NOPROD = EZ_TILED_NOPROD != 0;
+__host__ __device__ constexpr int win_pitch(int w, int ni) { return (w + 3) + ((((ni - (w + 3)) % 4) + 4) % 4); }
+__host__ __device__ constexpr int win_cap(int w, int h) { return TILED_NOPROD ? (w + 6) * h + 8 : (w | 1) * h; }   // levels of a stage evaluated per loop iteration in the window kernel
 constexpr int TILE_CAP = EZ_TILE_CAP;     // floats per shared-memory buffer
 constexpr int LPS = EZ_LPS;               // source levels per pipeline stage (one CTA barrier per stage)
 constexpr int NSTAGE = EZ_NSTAGE;          // buffers per CTA: the producer warp runs NSTAGE-1 source levels ahead of the compute warps
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     // the box holds every fast thread's full window; a window may overhang the field by one column/row on the
     // high side (that column/row carries zero weights) -- stage_tile replicates the field edge there
     const int w = c1 - c0 + 1, h = r1 - r0 + 1;
-    const bool box_ok = (c0 != INT_MAX) && w <= 64 && (long)(w | 1) * h <= TILE_CAP;
+    const bool box_ok = (c0 != INT_MAX) && w <= 64 && (long)win_cap(w, h) <= TILE_CAP && (!TILED_NOPROD || rowsep || h * ((w + 6) >> 2) <= 2 * TT * TT);
     const bool fast = (rowsep ? k.elig : k.fast) && box_ok;
     const unsigned int ballot = __ballot_sync(0xffffffffu, fast);
     if ((threadIdx.x & 31) == 0) flags[tile * 8 + (threadIdx.x >> 5)] = ballot;
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
         td.panel = tile_panel; td.nfast = s_cnt[1]; td.nslow = s_cnt[0]; td.kind = (rowsep && box_ok) ? 1 : 0;
         tiles[tile] = td;
         atomicAdd(counters + 0, (unsigned int)s_cnt[0]);
-        if (box_ok && s_cnt[1] > 0 && td.kind == 0) atomicMax(counters + 2, (unsigned int)((w | 1) * h));
+        if (box_ok && s_cnt[1] > 0 && td.kind == 0) atomicMax(counters + 2, (unsigned int)win_cap(w, h));
         if (s_cnt[1] > 0) atomicAdd(counters + 1, 1u);
         if (td.kind == 1 && s_cnt[1] > 0) {
             atomicMax(counters + 3, (unsigned int)w);
@@ -404,15 +412,186 @@ __device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// EZ_TILED_NOPROD variant: same arithmetic, staging by every thread (16-byte cp.async), one barrier per stage
+// ---------------------------------------------------------------------------------------------------
+constexpr int NTHR_WIN = TILED_NOPROD ? TT * TT : NTHR_TILED;
+
 template <int DEG>
-__global__ void __launch_bounds__(NTHR_TILED, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) {
+__device__ __forceinline__ void window_all(const GridDev &g, const InterpArgs &a, const TileDesc &td, const Quad &q, bool fast,
+                                           const float *__restrict__ zin, int src_rows, float *__restrict__ smem) {
+    constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
+    const int ni = a.out_ni, nj = a.out_nj;
+    const int pitch = win_pitch(td.w, g.ni);
+    float2 wxp[2][W], wyp[2][W], smp[2];   // [pair][k] = (weight of point 2*pair, weight of point 2*pair+1)
+    bool valid[4] = {false, false, false, false};
+    int base = 0;
+    if (fast) {
+        int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
+        float tx[4][4], ty[4][4], sm1[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            valid[p] = q.valid(p, ni, nj);
+            c0[p] = INT_MAX; r0[p] = INT_MAX; sm1[p] = 0.f;
+            if (valid[p]) {
+                const int n = q.index(p, ni);
+                point_plan<DEG>(g, a.x[n], a.y[n], c0[p], r0[p], tx[p], ty[p], sm1[p]);
+                wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
+            }
+        }
+        float wx[4][W], wy[4][W];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const bool sx = valid[p] && (c0[p] != wc0), sy = valid[p] && (r0[p] != wr0);   // offset 0 or 1 inside the window
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const float lo = (k < S) ? tx[p][k] : 0.f, hi = (k > 0) ? tx[p][k - 1] : 0.f;
+                wx[p][k] = valid[p] ? (sx ? hi : lo) : 0.f;
+                const float lo2 = (k < S) ? ty[p][k] : 0.f, hi2 = (k > 0) ? ty[p][k - 1] : 0.f;
+                wy[p][k] = valid[p] ? (sy ? hi2 : lo2) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < 2; pp++) {
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                wxp[pp][k] = make_float2(wx[2 * pp][k], wx[2 * pp + 1][k]);
+                wyp[pp][k] = make_float2(wy[2 * pp][k], wy[2 * pp + 1][k]);
+            }
+            smp[pp] = make_float2(sm1[2 * pp], sm1[2 * pp + 1]);
+        }
+        base = (wr0 - td.r0) * pitch + (wc0 - td.c0);
+    }
+    const int nf = a.nfields;
+    const long os = a.out_stride, is = a.in_stride;
+    // float2 stores need all four points and 8-byte alignment (even target row length; q.ox is even)
+    const bool full = fast && ((ni & 1) == 0) && valid[3] && ((reinterpret_cast<uintptr_t>(a.zout) & 7) == 0) && ((os & 1) == 0);
+    float *w0 = a.zout + (long)q.oy * ni + q.ox;
+    const int cap = a.tile_cap;
+    const int nstages = (nf + LPS - 1) / LPS;
+
+    // ---- copy side (see ez_interp_rowsep.cuh): box element (r, j) of level l of a stage at float offset delta_l + r pitch + j
+    // of the level's buffer, delta_l = (float index in memory of source element (r0, c0)) mod 4; thread t copies chunks t and
+    // t + 256 of each level (chunk = row t / nck, 16-byte chunk t % nck of that row).
+    const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t capB = (uint32_t)cap * 4u;
+    const int nrow = min(td.h, src_rows - td.r0);
+    const int nck = (td.w + 6) >> 2;
+    unsigned int dpk = 0u;
+    int cj[2] = {0, 0}, crowoff[2] = {0, 0};
+    unsigned int cvalid = 0u;     // bit 4 k + l: slot k, level l
+    uint32_t cbase[2] = {0u, 0u};
+    {
+        const float *lvl0 = zin + (long)td.r0 * g.ni + td.c0;
+#pragma unroll
+        for (int l = 0; l < LPS; l++) dpk |= (unsigned int)((reinterpret_cast<uintptr_t>(lvl0 + l * is) >> 2) & 3u) << (2 * l);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int t = threadIdx.x + k * NTHR_WIN;
+            const int crow = t / nck, ck4 = 4 * (t - crow * nck);
+            crowoff[k] = (td.r0 + crow) * g.ni + td.c0 - 3;
+            cbase[k] = (uint32_t)(crow * pitch - 3) * 4u;
+#pragma unroll
+            for (int l = 0; l < LPS; l++) {
+                const int bm = (int)((dpk >> (2 * l)) & 3u) + crow * pitch;
+                const int j = ((bm & ~3) + ck4) - bm;
+                cj[k] |= (j + 3) << (8 * l);
+                if (crow < nrow && j < td.w) cvalid |= 1u << (4 * k + l);
+            }
+        }
+    }
+    auto sloff = [&](int l) { return (uint32_t)l * capB + ((dpk >> (2 * l)) & 3u) * 4u; };
+    auto issue = [&](int st) {
+        if (cvalid && st < nstages) {
+            const uint32_t sb = smem32 + (uint32_t)(st % NSTAGE) * (LPS * capB);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if ((cvalid >> (4 * k)) & 0xfu) {
+                    const float *p = zin + (long)(st * LPS) * is + crowoff[k];
+#pragma unroll
+                    for (int l = 0; l < LPS; l++) {
+                        if (((cvalid >> (4 * k + l)) & 1u) && st * LPS + l < nf) {
+                            const uint32_t jb = (uint32_t)(cj[k] >> (8 * l)) & 0xffu;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + cbase[k] + sloff(l) + 4u * jb), "l"(p + jb) : "memory");
+                        }
+                        p += is;
+                    }
+                }
+            }
+        }
+        __pipeline_commit();
+    };
+#pragma unroll 1
+    for (int k = 0; k < NSTAGE; k++) issue(k);
+    __pipeline_wait_prior(NSTAGE - 1);
+    __syncthreads();
+
+    int slot = 0;
+#pragma unroll 1
+    for (int st = 0; st < nstages; st++) {
+        const float *sbase = smem + slot * LPS * cap + base;
+        const int nl = min(LPS, nf - st * LPS);
+        if (fast) {
+#pragma unroll TILED_UNROLL
+            for (int l = 0; l < nl; l++) {
+                const float *s = sbase + l * cap + ((dpk >> (2 * l)) & 3u);
+                const float zc = s[(W / 2) * pitch + W / 2];
+                const float2 zc2 = make_float2(zc, zc);
+                float2 acc[2];
+#pragma unroll
+                for (int r = 0; r < W; r++) {
+                    float2 d[W];
+#pragma unroll
+                    for (int c = 0; c < W; c++) {
+                        const float v = s[r * pitch + c] - zc;
+                        d[c] = make_float2(v, v);
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        float2 rs = __fmul2_rn(wxp[pp][0], d[0]);
+#pragma unroll
+                        for (int c = 1; c < W; c++) rs = __ffma2_rn(wxp[pp][c], d[c], rs);
+                        acc[pp] = (r == 0) ? __fmul2_rn(wyp[pp][0], rs) : __ffma2_rn(wyp[pp][r], rs, acc[pp]);
+                    }
+                }
+                const float2 r01 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[0], acc[0]));
+                const float2 r23 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[1], acc[1]));
+                float *w1 = w0 + ni;
+                if (full) {
+                    *reinterpret_cast<float2 *>(w0) = r01;
+                    *reinterpret_cast<float2 *>(w1) = r23;
+                } else {
+                    if (valid[0]) w0[0] = r01.x;
+                    if (valid[1]) w0[1] = r01.y;
+                    if (valid[2]) w1[0] = r23.x;
+                    if (valid[3]) w1[1] = r23.y;
+                }
+                w0 += os;
+            }
+        }
+        __pipeline_wait_prior(NSTAGE - 2);   // stage st + 1 has landed (this thread's share)
+        __syncthreads();                     // ... everybody's, and everybody is done reading stage st
+        issue(st + NSTAGE);                  // refill the slot just read
+        if (++slot == NSTAGE) slot = 0;
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int by = remap_tile_row(blockIdx.y, gridDim.y);
     const int tile = by * gridDim.x + blockIdx.x;
     const TileDesc td = a.tiles[tile];
     if (td.nfast == 0 || td.kind != 0) return;   // kind 1: the row-separable kernel owns the tile
-    for (int k = threadIdx.x; k < NSTAGE * LPS * a.tile_cap; k += NTHR_TILED) smem[k] = 0.f;
+    for (int k = threadIdx.x; k < NSTAGE * LPS * a.tile_cap; k += NTHR_WIN) smem[k] = 0.f;
     __syncthreads();
+    if (TILED_NOPROD) {
+        const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
+        const Quad q = quad_of_thread(blockIdx.x, by);
+        if (td.panel) window_all<DEG>(a.src2, a, td, q, fast, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem);
+        else window_all<DEG>(a.src, a, td, q, fast, a.zin, a.src.j2 - a.src.j1 + 1, smem);
+        return;
+    }
     if (threadIdx.x >= TT * TT) {
         if (td.panel) producer_warp(a, a.zin + a.panel_stride, td, a.src2.ni, a.src2.j2 - a.src2.j1 + 1, smem, td.w | 1, a.tile_cap);
         else producer_warp(a, a.zin, td, a.src.ni, a.src.j2 - a.src.j1 + 1, smem, td.w | 1, a.tile_cap);
