@@ -722,13 +722,13 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         const int rs_p = rs_pitch(a.src.ni);
         InterpArgs ar = a;
         ar.tile_cap_rs = rs_cap(rs_p, a.tile_cap_rs);   // a.tile_cap_rs arrives as the tallest box height
-        const size_t smem_rs = (size_t)RS_NSTAGE * LPS * ar.tile_cap_rs * sizeof(float) + 2 * (size_t)TO * RS_VP * sizeof(float4) + 64;
+        const size_t smem_rs = (size_t)RS_NSTAGE * LPS * ar.tile_cap_rs * sizeof(float) + 2 * (size_t)TO * RS_VP * sizeof(float4) + TO * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
             const int mx = NSTAGE * LPS * TILE_CAP * (int)sizeof(float);
             cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            const int mxr = RS_NSTAGE * LPS * (TILE_CAP + 16) * (int)sizeof(float) + 2 * TO * RS_VP * (int)sizeof(float4) + 64;
+            const int mxr = RS_NSTAGE * LPS * (TILE_CAP + 16) * (int)sizeof(float) + 2 * TO * RS_VP * (int)sizeof(float4) + TO * (int)sizeof(double);
 #define EZ_RS_ATTR(P)                                                                                       \
     cudaFuncSetAttribute(k_interp_rowsep<3, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxr); \
     cudaFuncSetAttribute(k_interp_rowsep<1, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxr);

@@ -149,44 +149,56 @@ __device__ __forceinline__ void cubic_weights(double d, double w[4]) {
     w[3] = (c6 * d * d - c6) * d;
 }
 
+// PART: 0 = both axes ; 1 = the x side only (c[], wx ; py ignored) ; 2 = the y side only (r0, wy ; px ignored).
+// The two sides are independent in the reference too (ez_rgdint_3_*, ez_irgdint_3_*): the split only skips work.
+template <int PART = 0>
 __device__ __forceinline__ PlanCub plan_cubic(const GridDev &g, float px, float py) {
     PlanCub p;
+    constexpr bool DOX = PART != 2, DOY = PART != 1;
     const int ni = g.ni, j1 = g.j1, j2 = g.j2;
     p.ni = ni;
-    int i, im1, ip1, ip2;
-    const int j = min(j2 - 2, max(j1 + 1, f_ifix(py)));
-    if (is_irregular(g)) {
-        const int ny = j2 - j1 + 1;
-        const float *ay = g.ay - j1;
-        const float aym = __ldg(ay + j - 1), ay0 = __ldg(ay + j), ayp = __ldg(ay + j + 1);
-        const double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
-        double cx[6], cy[6];
-        float x1, x2, x3, x4;
-        int nxt;
-        if (g.ext == 0) {
-            i = min(g.i2 - 2, max(g.i1 + 1, f_ifix(px)));
-            im1 = i - 1; ip1 = i + 1; ip2 = i + 2;
-            x1 = __ldg(g.ax + im1 - 1); x2 = __ldg(g.ax + i - 1); x3 = __ldg(g.ax + ip1 - 1); x4 = __ldg(g.ax + ip2 - 1);
-            nxt = g.i2 - g.i1 + 1;
-        } else {
-            const int wrap = g.ext;
-            i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
-            seam_x(wrap, ni, g.ax, i, false, im1, ip1, ip2, x1, x2, x3, x4);
-            nxt = ni;
-        }
-        (void)x4;
-        const double x = (double)(x2 + (x3 - x2) * (px - (float)i));
+    int i = 1, im1 = 1, ip1 = 1, ip2 = 1;
+    const int j = DOY ? min(j2 - 2, max(j1 + 1, f_ifix(py))) : j1 + 1;
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            cx[k] = (double)__ldg(g.cx + (long)k * nxt + (i - 1));
-            cy[k] = (double)__ldg(g.cy + (long)k * ny + (j - j1));
+    for (int k = 0; k < 4; k++) { p.wx[k] = 0.0; p.wy[k] = 0.0; }
+    if (is_irregular(g)) {
+        if (DOY) {
+            const int ny = j2 - j1 + 1;
+            const float *ay = g.ay - j1;
+            const float aym = __ldg(ay + j - 1), ay0 = __ldg(ay + j), ayp = __ldg(ay + j + 1);
+            const double y = (double)(ay0 + (ayp - ay0) * (py - (float)j));
+            double cy[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) cy[k] = (double)__ldg(g.cy + (long)k * ny + (j - j1));
+            newton_weights(cy, y - (double)aym, y - (double)ay0, y - (double)ayp, p.wy);
         }
-        newton_weights(cx, x - (double)x1, x - (double)x2, x - (double)x3, p.wx);
-        newton_weights(cy, y - (double)aym, y - (double)ay0, y - (double)ayp, p.wy);
+        if (DOX) {
+            double cx[6];
+            float x1, x2, x3, x4;
+            int nxt;
+            if (g.ext == 0) {
+                i = min(g.i2 - 2, max(g.i1 + 1, f_ifix(px)));
+                im1 = i - 1; ip1 = i + 1; ip2 = i + 2;
+                x1 = __ldg(g.ax + im1 - 1); x2 = __ldg(g.ax + i - 1); x3 = __ldg(g.ax + ip1 - 1); x4 = __ldg(g.ax + ip2 - 1);
+                nxt = g.i2 - g.i1 + 1;
+            } else {
+                const int wrap = g.ext;
+                i = min(ni - 2 + wrap, max(1, max(2 - wrap, f_ifix(px))));
+                seam_x(wrap, ni, g.ax, i, false, im1, ip1, ip2, x1, x2, x3, x4);
+                nxt = ni;
+            }
+            (void)x4;
+            const double x = (double)(x2 + (x3 - x2) * (px - (float)i));
+#pragma unroll
+            for (int k = 0; k < 6; k++) cx[k] = (double)__ldg(g.cx + (long)k * nxt + (i - 1));
+            newton_weights(cx, x - (double)x1, x - (double)x2, x - (double)x3, p.wx);
+        }
     } else {
-        rgd3_cols(g.ext == 0 ? 0 : 1, ni, g.ext, px, i, im1, ip1, ip2);
-        cubic_weights((double)(px - (float)i), p.wx);
-        cubic_weights((double)(py - (float)j), p.wy);
+        if (DOX) {
+            rgd3_cols(g.ext == 0 ? 0 : 1, ni, g.ext, px, i, im1, ip1, ip2);
+            cubic_weights((double)(px - (float)i), p.wx);
+        }
+        if (DOY) cubic_weights((double)(py - (float)j), p.wy);
     }
     p.c[0] = im1 - 1; p.c[1] = i - 1; p.c[2] = ip1 - 1; p.c[3] = ip2 - 1;
     p.r0 = (j - 1 - j1) * ni;

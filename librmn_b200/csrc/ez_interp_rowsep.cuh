@@ -156,7 +156,8 @@ __device__ __forceinline__ void rowsep_phase2(const StageRef &zr, int nl, const 
 
 template <int DEG, int P>
 __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArgs &a, const TileDesc &td, int tile, int bx, int by,
-                                               const float *__restrict__ zin, int src_rows, uint32_t smem32, uint32_t vbuf32) {
+                                               const float *__restrict__ zin, int src_rows, uint32_t smem32, uint32_t vbuf32,
+                                               double *__restrict__ sumwy) {
     constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W, VP = RS_VP;
     const int ni = a.out_ni, nj = a.out_nj;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -173,9 +174,19 @@ __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArg
             const unsigned int yb = a.tile_rowy[tile * TO + 2 * wp + r];
             has[r] = yb != ROWY_NONE;
             if (has[r]) {
-                int c0;
-                float wx[4], s;
-                point_plan<DEG>(g, (float)(g.i1 + 1), __uint_as_float(yb), c0, r0[r], wx, wy[r], s);
+                double sw = 1.0;
+                if (DEG == 3) {   // the y side only; sum wy goes to shared memory for the point plans (s = sum wx sum wy - 1)
+                    const PlanCub pc = plan_cubic<2>(g, 0.f, __uint_as_float(yb));
+                    r0[r] = pc.r0 / pc.ni;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) wy[r][k] = (float)pc.wy[k];
+                    sw = pc.wy[0] + pc.wy[1] + pc.wy[2] + pc.wy[3];
+                } else {
+                    int c0;
+                    float wx[4], s;
+                    point_plan<DEG>(g, (float)(g.i1 + 1), __uint_as_float(yb), c0, r0[r], wx, wy[r], s);
+                }
+                if (lane == 0) sumwy[2 * wp + r] = sw;
             }
         }
         const int base = (has[0] || has[1]) ? min(r0[0], r0[1]) : td.r0;
@@ -191,6 +202,7 @@ __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArg
         }
     }
     const uint32_t vst0 = vbuf32 + (uint32_t)((2 * wp) * VP + lane) * 16u;
+    __syncthreads();   // sumwy of every tile row is in shared memory
 
     // ---- phase-2 plan: lane = target column of the tile, rows wp and wp + 16 ----
     float wxa[2][S], sm1[2];
@@ -209,7 +221,15 @@ __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArg
             const int n = oj * ni + oi;
             int c0, r0;
             float wx[4], wy[4];
-            point_plan<DEG>(g, a.x[n], a.y[n], c0, r0, wx, wy, sm1[k]);
+            if (DEG == 3) {   // the x side only
+                const PlanCub pc = plan_cubic<1>(g, a.x[n], 0.f);
+                c0 = pc.c[0];
+#pragma unroll
+                for (int c = 0; c < 4; c++) wx[c] = (float)pc.wx[c];
+                sm1[k] = (float)((pc.wx[0] + pc.wx[1] + pc.wx[2] + pc.wx[3]) * sumwy[jj] - 1.0);
+            } else {
+                point_plan<DEG>(g, a.x[n], a.y[n], c0, r0, wx, wy, sm1[k]);
+            }
 #pragma unroll
             for (int c = 0; c < S; c++) wxa[k][c] = wx[c];
             vld0[k] = vbuf32 + (uint32_t)(jj * VP + (c0 - td.c0)) * 16u;
@@ -312,8 +332,9 @@ __global__ void __launch_bounds__(RS_NTHR, EZ_ROWSEP_MINB) k_interp_rowsep(const
     __syncthreads();
     const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t vbuf32 = smem32 + (uint32_t)nstage_floats * 4u;
-    if (td.panel) rowsep_compute<DEG, P>(a.src2, a, td, tile, blockIdx.x, by, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32, vbuf32);
-    else rowsep_compute<DEG, P>(a.src, a, td, tile, blockIdx.x, by, a.zin, a.src.j2 - a.src.j1 + 1, smem32, vbuf32);
+    double *sumwy = reinterpret_cast<double *>(smem + nstage_floats + 2 * TO * RS_VP * 4);   // 32 doubles after the two V buffers
+    if (td.panel) rowsep_compute<DEG, P>(a.src2, a, td, tile, blockIdx.x, by, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32, vbuf32, sumwy);
+    else rowsep_compute<DEG, P>(a.src, a, td, tile, blockIdx.x, by, a.zin, a.src.j2 - a.src.j1 + 1, smem32, vbuf32, sumwy);
 }
 
 }  // namespace
