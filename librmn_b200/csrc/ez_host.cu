@@ -636,6 +636,32 @@ Gset *ensure_gset(Grid &out, Grid &in) {
     return gs;
 }
 
+// The tile kernels stage source rows in whole 16-byte blocks: up to 12 bytes before the first and after the last
+// element of the source fields are read.  That is inside the caller's allocation for every CUDA allocator (256-byte
+// granularity) unless the fields are a tight sub-range at the very edge of it; ask the driver for the allocation's
+// range and keep the per-point kernel when the 16-byte blocks would leave it (or when the driver cannot tell).
+bool source_blocks_inside_allocation(const float *d_zin, size_t nbytes) {
+    typedef int (*get_range_fn)(unsigned long long *, size_t *, unsigned long long);
+    static get_range_fn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (get_range_fn)p;
+        else
+            (void)cudaGetLastError();
+    }
+    if (!fn) return false;
+    unsigned long long base = 0;
+    size_t size = 0;
+    const unsigned long long lo = (unsigned long long)(uintptr_t)d_zin & ~15ull;
+    const unsigned long long hi = ((unsigned long long)(uintptr_t)d_zin + nbytes + 15ull) & ~15ull;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)d_zin) != 0) return false;
+    return lo >= base && hi <= base + size;
+}
+
 // Tile plan for the current (degree, zones) of `a` on this gridset; built on first use, kept in HBM.
 TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     TilePlan &tp = gs.plans[(a.o.degree == EZ_CUBIC ? 2 : 0) + (a.use_zones ? 1 : 0)];
@@ -810,7 +836,8 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     }
     a.out_ni = out.ni;
     a.out_nj = out.nj;
-    if (ezk::tiled_eligible(a)) {
+    const size_t in_bytes = ((size_t)(nfields - 1) * (size_t)in_stride + (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)in.ni * in.nj)) * sizeof(float);
+    if (ezk::tiled_eligible(a) && source_blocks_inside_allocation(d_zin, in_bytes)) {
         TilePlan *tp = ensure_tileplan(*gs, a);
         if (!tp) return -1;
         if (tp->suitable) {

@@ -500,3 +500,4 @@ def test_rowsep_levels_alignment_and_offsets(ezb, cuda_ok, degree):
             # (a tile whose reference cell holds the marker falls back to the plain fp32 weight form: error ~1e-6 of the MAGNITUDE)
             ulp_out = float(np.spacing(np.float32(np.abs(fields[np.abs(fields) < 1e20]).max())))   # the outputs are fp32: two correct roundings may differ by one ulp
             assert d.max().item() < (2e-5 if marker else 3e-6) * rng + ulp_out, (ni_src, nf, shift, offset, marker, d.max().item() / rng)
+
