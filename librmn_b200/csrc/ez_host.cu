@@ -60,6 +60,8 @@ struct Gset {   // _gridset, ez_def.h:148-166, device-resident
     bool yy = false;            // source is a 'U' supergrid: zb carries the panel bit, no zones
     float *d_x = nullptr, *d_y = nullptr;
     uint8_t *d_zb = nullptr;
+    int *d_perm = nullptr;      // 'Y' cloud targets: the points sorted by source cell (gather locality), built on first use
+    bool perm_tried = false;
     int counts[6] = {0, 0, 0, 0, 0, 0};   // DEHORS, AU_NORD, AU_SUD, POLE_NORD, POLE_SUD, yang
 };
 
@@ -725,6 +727,8 @@ void free_gset(Gset &gs) {
     if (gs.d_x) cudaFree(gs.d_x);
     if (gs.d_y) cudaFree(gs.d_y);
     if (gs.d_zb) cudaFree(gs.d_zb);
+    if (gs.d_perm) cudaFree(gs.d_perm);
+    gs.d_perm = nullptr; gs.perm_tried = false;
     gs.d_x = gs.d_y = nullptr;
     gs.d_zb = nullptr;
     gs.built = false;
@@ -852,6 +856,24 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.list = tp->d_list;
             a.nlist = tp->nlist;
         }
+    }
+    // scattered ('Y' cloud) targets arrive in arbitrary order: the per-point kernel walks them sorted by source cell
+    if (!a.tiles && out.grtyp == 'Y' && a.o.arith >= 1 && a.npts >= 32768) {
+        if (!gs->perm_tried) {
+            gs->perm_tried = true;
+            if (cudaMalloc((void **)&gs->d_perm, (size_t)a.npts * sizeof(int)) == cudaSuccess) {
+                const GridDev &sg = a.src;
+                if (!ezk::sort_points_by_cell(gs->d_x, gs->d_y, a.yy ? gs->d_zb : nullptr, sg.ni, sg.j2 - sg.j1 + 1, a.npts, gs->d_perm, S.stream)) {
+                    cudaFree(gs->d_perm);
+                    gs->d_perm = nullptr;
+                }
+                S.launches += 2;
+            } else {
+                gs->d_perm = nullptr;
+                (void)cudaGetLastError();
+            }
+        }
+        if (gs->d_perm) { a.list = gs->d_perm; a.nlist = a.npts; }
     }
     S.last_path = a.tiles ? ((a.ntiles_window > 0 ? 2 : 0) | (a.nlist > 0 ? 4 : 0) | (a.ntiles_rowsep > 0 ? 8 : 0)) : 1;
     S.last_nlist = a.tiles ? a.nlist : 0;

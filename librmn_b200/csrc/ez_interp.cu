@@ -15,6 +15,7 @@
 //      weights evaluated once per point in fp64 and applied with fp64 FMAs per level.
 // Compiled with -fmad=false; the weight form uses explicit fma().
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <limits.h>
 #include <math.h>
 #include "ez_kernels.h"
@@ -660,6 +661,21 @@ __global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj,
     for (int i = 0; i < ni; i++) row[i] = moyenne;
 }
 
+// sort key of a target point = the source cell (and panel) its stencil starts in: threads that are neighbours after the
+// sort gather from the same 32-byte sectors (scattered 'Y' cloud targets arrive in arbitrary order)
+__global__ void k_cell_keys(const float *__restrict__ x, const float *__restrict__ y, const uint8_t *__restrict__ zb, int ni, int nj, int npts,
+                            unsigned int *__restrict__ keys, int *__restrict__ vals) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npts) return;
+    const int i = min(ni - 1, max(0, (int)x[n] - 1)), j = min(nj - 1, max(0, (int)y[n] - 1));
+    // 8 x 4-cell blocks in row-major order keep both stencil rows and columns close
+    unsigned int key = (unsigned int)(j >> 2) * (unsigned int)((ni + 7) >> 3) + (unsigned int)(i >> 3);
+    key = key * 32u + (unsigned int)((j & 3) * 8 + (i & 7));
+    if (zb && (zb[n] & ZB_YANG)) key += 0x80000000u;
+    keys[n] = key;
+    vals[n] = n;
+}
+
 }  // namespace
 
 #include "ez_interp_fast.cuh"
@@ -680,6 +696,27 @@ void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldSc
         k_minmax<<<grid, TPB, 0, s>>>(a, scratch);
     }
     k_field_scalars<<<2 * a.nfields, 256, 0, s>>>(a, need_poles, need_minmax, fs, scratch);
+}
+
+// permutation of the target points by source cell (device array of npts ints); returns false when scratch memory is not available
+bool sort_points_by_cell(const float *x, const float *y, const uint8_t *zb, int ni, int nj, int npts, int *perm, cudaStream_t s) {
+    unsigned int *keys_in = nullptr, *keys_out = nullptr;
+    int *vals_in = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    bool ok = false;
+    if (cudaMalloc((void **)&keys_in, (size_t)npts * 4) == cudaSuccess && cudaMalloc((void **)&keys_out, (size_t)npts * 4) == cudaSuccess &&
+        cudaMalloc((void **)&vals_in, (size_t)npts * 4) == cudaSuccess) {
+        k_cell_keys<<<(npts + 255) / 256, 256, 0, s>>>(x, y, zb, ni, nj, npts, keys_in, vals_in);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, perm, npts, 0, 32, s);
+        if (cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16) == cudaSuccess) {
+            ok = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, perm, npts, 0, 32, s) == cudaSuccess &&
+                 cudaStreamSynchronize(s) == cudaSuccess;
+        }
+    }
+    if (!ok) (void)cudaGetLastError();
+    cudaFree(keys_in); cudaFree(keys_out); cudaFree(vals_in); cudaFree(tmp);
+    return ok;
 }
 
 bool tiled_eligible(const InterpArgs &a) {

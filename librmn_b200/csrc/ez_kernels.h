@@ -90,6 +90,8 @@ struct InterpFork {
     cudaEvent_t ev_fork, ev_join[2];
 };
 int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing = nullptr, const InterpFork *fork = nullptr);
+// scattered targets: permutation of the target points by source cell, for gather locality in the per-point kernel
+bool sort_points_by_cell(const float *x, const float *y, const uint8_t *zb, int ni, int nj, int npts, int *perm, cudaStream_t s);
 // tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry
 bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);

@@ -501,3 +501,22 @@ def test_rowsep_levels_alignment_and_offsets(ezb, cuda_ok, degree):
             ulp_out = float(np.spacing(np.float32(np.abs(fields[np.abs(fields) < 1e20]).max())))   # the outputs are fp32: two correct roundings may differ by one ulp
             assert d.max().item() < (2e-5 if marker else 3e-6) * rng + ulp_out, (ni_src, nf, shift, offset, marker, d.max().item() / rng)
 
+
+
+@pytest.mark.parametrize("degree", ["nearest", "linear", "cubic"])
+def test_large_cloud_target_sorted_by_source_cell(ezb, ezref, cuda_ok, degree):
+    """'Y' cloud targets of 32768 points or more are processed in source-cell order (a permutation built once per
+    gridset); the results must not depend on it: nearest picks bit-exact, values within tolerance of the oracle."""
+    ezb.set_arith(2)
+    outs = []
+    for lib in (ezb, ezref):
+        c = configs.c4(lib, 400, 200, 50000, degree)
+        c.defset()
+        z = np.full(c.dst_shape, -7.0, np.float32)
+        assert lib.ezsint(z, c.source()) >= 0
+        outs.append(z)
+    rng = float(outs[1].max() - outs[1].min())
+    if degree == "nearest":
+        assert int((outs[0] != outs[1]).sum()) <= 5     # exact coordinate ties only
+    else:
+        assert float(np.abs(outs[0].astype(np.float64) - outs[1]).max()) / rng < TOL
