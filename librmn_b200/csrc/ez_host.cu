@@ -840,8 +840,10 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     }
     a.out_ni = out.ni;
     a.out_nj = out.nj;
-    const size_t in_bytes = ((size_t)(nfields - 1) * (size_t)in_stride + (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)in.ni * in.nj)) * sizeof(float);
-    if (ezk::tiled_eligible(a) && source_blocks_inside_allocation(d_zin, in_bytes)) {
+    // (fields of one call may come from different allocations -- the fused (u, v) launch --, so the first and the last are checked)
+    const size_t field_bytes = (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)in.ni * in.nj) * sizeof(float);
+    if (ezk::tiled_eligible(a) && source_blocks_inside_allocation(d_zin, field_bytes) &&
+        (nfields == 1 || source_blocks_inside_allocation(d_zin + (long)(nfields - 1) * in_stride, field_bytes))) {
         TilePlan *tp = ensure_tileplan(*gs, a);
         if (!tp) return -1;
         if (tp->suitable) {
@@ -1123,8 +1125,15 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
                 }
             }
         }
-        r1 = sint_dev(out, *eff_in, d_uo, ui, nfields, in_stride, out_stride, 1, +1, prow_u);
-        r2 = sint_dev(out, *eff_in, d_vo, vi, nfields, in_stride, out_stride, 1, -1, prow_v);
+        if (nfields == 1 && !prow_u && !prow_v && !eff_in->needs_expansion) {
+            // one (u, v) pair, no synthetic pole rows, no hemispheric mirror (the only place the two components are treated
+            // differently): ONE launch over two "fields" whose stride is the distance between the caller's arrays, so the
+            // gridset, the plans and the tile setup are read and built once for both components
+            r1 = r2 = sint_dev(out, *eff_in, d_uo, ui, 2, (long)(vi - ui), (long)(d_vo - d_uo), 1, +1, nullptr);
+        } else {
+            r1 = sint_dev(out, *eff_in, d_uo, ui, nfields, in_stride, out_stride, 1, +1, prow_u);
+            r2 = sint_dev(out, *eff_in, d_vo, vi, nfields, in_stride, out_stride, 1, -1, prow_v);
+        }
         if (r1 < 0 || r2 < 0) return -1;
     }
     if (wind_dev(out, *eff_in, d_uo, d_vo, nfields, out_stride, mode) < 0) return -1;
