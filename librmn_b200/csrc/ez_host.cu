@@ -60,6 +60,8 @@ struct Gset {   // _gridset, ez_def.h:148-166, device-resident
     bool yy = false;            // source is a 'U' supergrid: zb carries the panel bit, no zones
     float *d_x = nullptr, *d_y = nullptr;
     uint8_t *d_zb = nullptr;
+    float4 *d_wrot = nullptr;   // c_ezuvint: per-point rotation matrix of the (u,v) -> (u,v) wind conversion, built on first use
+    bool wrot_tried = false;
     int *d_perm = nullptr;      // 'Y' cloud targets: the points sorted by source cell (gather locality), built on first use
     bool perm_tried = false;
     int counts[6] = {0, 0, 0, 0, 0, 0};   // DEHORS, AU_NORD, AU_SUD, POLE_NORD, POLE_SUD, yang
@@ -728,6 +730,8 @@ void free_gset(Gset &gs) {
     if (gs.d_y) cudaFree(gs.d_y);
     if (gs.d_zb) cudaFree(gs.d_zb);
     if (gs.d_perm) cudaFree(gs.d_perm);
+    if (gs.d_wrot) cudaFree(gs.d_wrot);
+    gs.d_wrot = nullptr; gs.wrot_tried = false;
     gs.d_perm = nullptr; gs.perm_tried = false;
     gs.d_x = gs.d_y = nullptr;
     gs.d_zb = nullptr;
@@ -1053,6 +1057,25 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
     w.nfields = nfields;
     w.npts = out.ni * out.nj;
     w.mode = mode;
+    if (mode == 0 && S.arith >= 1 && in.id != out.id) {   // cached rotation (ez_wind.cu); arith 0 keeps the reference's per-call evaluation
+        Gset *gs = ensure_gset(out, in);
+        if (gs && !gs->wrot_tried) {
+            gs->wrot_tried = true;
+            if (cudaMalloc((void **)&gs->d_wrot, (size_t)w.npts * sizeof(float4)) == cudaSuccess) {
+                if (!ezk::wind_matrix(w, gs->d_wrot, S.stream)) { cudaFree(gs->d_wrot); gs->d_wrot = nullptr; }
+                S.launches += 3;
+            } else {
+                gs->d_wrot = nullptr;
+                (void)cudaGetLastError();
+            }
+        }
+        if (gs && gs->d_wrot) {
+            ezk::wind_apply(gs->d_wrot, d_u, d_v, stride, nfields, w.npts, S.stream);
+            S.launches++;
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     ezk::wind(w, S.stream);
     S.launches++;
     CUDA_OK(cudaGetLastError());

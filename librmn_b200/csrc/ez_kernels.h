@@ -102,6 +102,9 @@ void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask
                    int linear, cudaStream_t s);
 // K17 wind rotation
 void wind(const WindArgs &a, cudaStream_t s);
+// cached per-point rotation of the (u,v) -> (u,v) conversion: build once per gridset, apply per call
+bool wind_matrix(const WindArgs &a, float4 *m, cudaStream_t s);
+void wind_apply(const float4 *m, float *u, float *v, long stride, int nfields, int npts, cudaStream_t s);
 // K18 synthetic pole rows for vectors (ez_calcnpolarwind.c / ez_calcspolarwind.c)
 void polar_wind_rows(const PolarWindArgs &a, cudaStream_t s);
 // B-grid pole-row averaging, ez_corrbgd.inc:29-52

@@ -235,7 +235,57 @@ __global__ void __launch_bounds__(256) k_polar_wind(PolarWindArgs a) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// Cached rotation.  For (u, v) -> (u, v) the chain above is, at every target point, a rotation by an angle that depends
+// on the point only: linear in (u, v).  Its matrix is obtained by pushing the unit vectors (1, 0) and (0, 1) through
+// k_wind itself (so every grid-type case is covered by construction) and kept per gridset; later calls stream
+// 16 B of matrix per point instead of redoing the trigonometry.  Differs from the per-call evaluation by a few 1e-7
+// of the wind speed; the reference-order mode (arith 0) does not use it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_wind_unit(float *__restrict__ u, float *__restrict__ v, long stride, int npts) {
+    const int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= npts) return;
+    u[n] = 1.f; v[n] = 0.f;
+    u[stride + n] = 0.f; v[stride + n] = 1.f;
+}
+__global__ void __launch_bounds__(TPB) k_wind_pack(const float *__restrict__ u, const float *__restrict__ v, long stride, int npts, float4 *__restrict__ m) {
+    const int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= npts) return;
+    m[n] = make_float4(u[n], u[stride + n], v[n], v[stride + n]);   // u' = x u + y v ; v' = z u + w v
+}
+__global__ void __launch_bounds__(TPB) k_wind_apply(const float4 *__restrict__ m, float *__restrict__ u, float *__restrict__ v, long stride, int nfields,
+                                                    int npts) {
+    const int n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= npts) return;
+    const float4 r = m[n];
+#pragma unroll 4
+    for (int f = 0; f < nfields; f++) {
+        const long k = (long)f * stride + n;
+        const float a = u[k], b = v[k];
+        u[k] = fmaf(r.y, b, r.x * a);
+        v[k] = fmaf(r.w, b, r.z * a);
+    }
+}
+
 namespace ezk {
+bool wind_matrix(const WindArgs &a0, float4 *m, cudaStream_t s) {
+    float *tmp = nullptr;
+    const size_t n = (size_t)a0.npts;
+    if (cudaMalloc((void **)&tmp, 4 * n * sizeof(float)) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    WindArgs a = a0;
+    a.u = tmp; a.v = tmp + 2 * n; a.stride = (long)n; a.nfields = 2; a.mode = 0;
+    const int nb = (a.npts + TPB - 1) / TPB;
+    k_wind_unit<<<nb, TPB, 0, s>>>(a.u, a.v, a.stride, a.npts);
+    k_wind<<<nb, TPB, 0, s>>>(a);
+    k_wind_pack<<<nb, TPB, 0, s>>>(a.u, a.v, a.stride, a.npts, m);
+    const bool ok = cudaStreamSynchronize(s) == cudaSuccess;
+    cudaFree(tmp);
+    return ok;
+}
+void wind_apply(const float4 *m, float *u, float *v, long stride, int nfields, int npts, cudaStream_t s) {
+    if (npts <= 0 || nfields <= 0) return;
+    k_wind_apply<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(m, u, v, stride, nfields, npts);
+}
 void polar_wind_rows(const PolarWindArgs &a, cudaStream_t s) {
     if (a.nfields <= 0) return;
     k_polar_wind<<<2 * a.nfields, 256, 0, s>>>(a);
