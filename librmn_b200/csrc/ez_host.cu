@@ -51,6 +51,11 @@ struct TilePlan {   // classification of the target points for the tiled kernel 
     unsigned int *d_rowy = nullptr;   // row-separable tiles: y of each target row (ez_interp_rowsep.cuh)
     int nlist = 0, ntiles_fast = 0, cap = 0;
     int ntiles_rowsep = 0, vw = 0, cap_rs = 0;
+    // plan cache (ez_interp_tiled.cuh: k_plan_cache): stencil origin, fp32 weights and s of every target point
+    int *d_pc_idx = nullptr;
+    float4 *d_pc_wx = nullptr, *d_pc_wy = nullptr;
+    float *d_pc_sm1 = nullptr;
+    bool pc_tried = false;
 };
 
 struct Gset {   // _gridset, ez_def.h:148-166, device-resident
@@ -718,12 +723,35 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     return &tp;
 }
 
+// Plan cache of a tile plan, built on the first launch that wants it (see sint_dev): 40 B per target point.
+void ensure_plan_cache(TilePlan &tp, const InterpArgs &a) {
+    if (tp.pc_tried) return;
+    tp.pc_tried = true;
+    static const bool pc_on = !(getenv("EZB200_PLAN_CACHE") && atoi(getenv("EZB200_PLAN_CACHE")) == 0);
+    if (tp.suitable && pc_on && a.src.ni < 65536 && (a.src.j2 - a.src.j1 + 1) < 32768 && (!a.yy || (a.src2.ni < 65536 && (a.src2.j2 - a.src2.j1 + 1) < 32768))) {
+        const size_t n = (size_t)a.npts;
+        if (cudaMalloc((void **)&tp.d_pc_idx, n * sizeof(int)) == cudaSuccess && cudaMalloc((void **)&tp.d_pc_wx, n * sizeof(float4)) == cudaSuccess &&
+            cudaMalloc((void **)&tp.d_pc_wy, n * sizeof(float4)) == cudaSuccess && cudaMalloc((void **)&tp.d_pc_sm1, n * sizeof(float)) == cudaSuccess) {
+            ezk::plan_cache(a, tp.d_pc_idx, tp.d_pc_wx, tp.d_pc_wy, tp.d_pc_sm1, S.stream);
+            S.launches++;
+        } else {   // not enough memory: the tile kernels recompute the plans
+            (void)cudaGetLastError();
+            cudaFree(tp.d_pc_idx); cudaFree(tp.d_pc_wx); cudaFree(tp.d_pc_wy); cudaFree(tp.d_pc_sm1);
+            tp.d_pc_idx = nullptr; tp.d_pc_wx = tp.d_pc_wy = nullptr; tp.d_pc_sm1 = nullptr;
+        }
+    }
+}
+
 void free_gset(Gset &gs) {
     for (auto &tp : gs.plans) {
         if (tp.d_tiles) cudaFree(tp.d_tiles);
         if (tp.d_flags) cudaFree(tp.d_flags);
         if (tp.d_list) cudaFree(tp.d_list);
         if (tp.d_rowy) cudaFree(tp.d_rowy);
+        if (tp.d_pc_idx) cudaFree(tp.d_pc_idx);
+        if (tp.d_pc_wx) cudaFree(tp.d_pc_wx);
+        if (tp.d_pc_wy) cudaFree(tp.d_pc_wy);
+        if (tp.d_pc_sm1) cudaFree(tp.d_pc_sm1);
         tp = TilePlan();
     }
     if (gs.d_x) cudaFree(gs.d_x);
@@ -855,6 +883,14 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.tile_flags = tp->d_flags;
             a.tile_cap = tp->cap;
             a.tile_rowy = tp->d_rowy;
+            // The cached plans pay when the plan arithmetic is heavy (Newton weights of irregular Z / # / G sources) or the
+            // launch has many levels to amortise nothing else over; a single field from a regular source recomputes them
+            // faster than it would read 40 B per point.
+            const bool irregular = a.yy || in.grtyp == 'Z' || in.grtyp == '#' || in.grtyp == 'G';
+            if (irregular || nfields >= 8) {
+                ensure_plan_cache(*tp, a);
+                a.pc_idx = tp->d_pc_idx; a.pc_wx = tp->d_pc_wx; a.pc_wy = tp->d_pc_wy; a.pc_sm1 = tp->d_pc_sm1;
+            }
             a.tile_vw = tp->vw;
             a.tile_cap_rs = tp->cap_rs;
             a.ntiles_rowsep = tp->ntiles_rowsep;

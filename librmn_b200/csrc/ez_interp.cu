@@ -747,6 +747,12 @@ void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned i
     k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor);
 }
 
+void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s) {
+    const int nb = (a.npts + 255) / 256;
+    if (a.o.degree == EZ_CUBIC) k_plan_cache<3><<<nb, 256, 0, s>>>(a, idx, wx, wy, sm1);
+    else k_plan_cache<1><<<nb, 256, 0, s>>>(a, idx, wx, wy, sm1);
+}
+
 int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, const InterpFork *fork) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
     if (a.tiles) {

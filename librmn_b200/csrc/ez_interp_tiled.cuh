@@ -247,6 +247,37 @@ __global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ I
     }
 }
 
+// third pass: the plan of every target point, stored for the tile kernels (40 B per point)
+template <int DEG>
+__global__ void __launch_bounds__(256) k_plan_cache(const __grid_constant__ InterpArgs a, int *__restrict__ idx, float4 *__restrict__ wxo,
+                                                    float4 *__restrict__ wyo, float *__restrict__ sm1o) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= a.npts) return;
+    const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
+    int c0 = 0, r0 = 0;
+    float wx[4] = {0.f, 0.f, 0.f, 0.f}, wy[4] = {0.f, 0.f, 0.f, 0.f}, s = 0.f;
+    if (a.yy && (bits & ZB_YANG)) point_plan<DEG>(a.src2, a.x[n], a.y[n], c0, r0, wx, wy, s);
+    else point_plan<DEG>(a.src, a.x[n], a.y[n], c0, r0, wx, wy, s);
+    idx[n] = (r0 << 16) | (c0 & 0xffff);
+    wxo[n] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+    wyo[n] = make_float4(wy[0], wy[1], wy[2], wy[3]);
+    sm1o[n] = s;
+}
+// a point's plan: from the cache when there is one, recomputed otherwise (bit-identical values)
+template <int DEG>
+__device__ __forceinline__ void cached_plan(const GridDev &g, const InterpArgs &a, int n, int &c0, int &r0, float wx[4], float wy[4], float &sm1) {
+    if (a.pc_idx) {
+        const int k = __ldg(a.pc_idx + n);
+        c0 = k & 0xffff; r0 = k >> 16;
+        const float4 X = __ldg(a.pc_wx + n), Y = __ldg(a.pc_wy + n);
+        wx[0] = X.x; wx[1] = X.y; wx[2] = X.z; wx[3] = X.w;
+        wy[0] = Y.x; wy[1] = Y.y; wy[2] = Y.z; wy[3] = Y.w;
+        sm1 = __ldg(a.pc_sm1 + n);
+    } else {
+        point_plan<DEG>(g, a.x[n], a.y[n], c0, r0, wx, wy, sm1);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------
@@ -435,7 +466,7 @@ __device__ __forceinline__ void window_all(const GridDev &g, const InterpArgs &a
             c0[p] = INT_MAX; r0[p] = INT_MAX; sm1[p] = 0.f;
             if (valid[p]) {
                 const int n = q.index(p, ni);
-                point_plan<DEG>(g, a.x[n], a.y[n], c0[p], r0[p], tx[p], ty[p], sm1[p]);
+                cached_plan<DEG>(g, a, n, c0[p], r0[p], tx[p], ty[p], sm1[p]);
                 wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
             }
         }

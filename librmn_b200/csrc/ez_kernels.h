@@ -34,6 +34,11 @@ struct InterpArgs {
     int tile_cap_rs;              // floats per staged source level in the row-separable kernel (pitch x tallest box)
     int ntiles_rowsep, ntiles_window;
     int rowsep_enable;            // classification only: allow tiles to be marked row-separable
+    // plan cache of the tile plan (per target point: stencil origin, fp32 x / y weights, s = sum wx sum wy - 1), or nullptr:
+    // the tile kernels then load 40 B per point instead of redoing the fp64 plan arithmetic in every launch
+    const int *pc_idx;            // (r0 << 16) | c0
+    const float4 *pc_wx, *pc_wy;
+    const float *pc_sm1;
     // per-point kernel restricted to a compacted list of target points (nullptr = all npts points)
     const int *list;
     int nlist;
@@ -97,6 +102,7 @@ bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
 void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *rowy, unsigned int *counters, cudaStream_t s);
 void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s);
+void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s);
 // K19 integer mask transfer
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,
                    int linear, cudaStream_t s);
