@@ -222,7 +222,7 @@ __device__ __forceinline__ void rowsep_compute(const GridDev &g, const InterpArg
             int c0, r0;
             float wx[4], wy[4];
             if (a.pc_idx) {   // plan cache of the tile plan
-                cached_plan<DEG>(g, a, n, c0, r0, wx, wy, sm1[k]);
+                cached_plan<DEG, false>(g, a, n, c0, r0, wx, wy, sm1[k]);
             } else if (DEG == 3) {   // the x side only
                 const PlanCub pc = plan_cubic<1>(g, a.x[n], 0.f);
                 c0 = pc.c[0];

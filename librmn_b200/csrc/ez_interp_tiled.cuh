@@ -264,14 +264,17 @@ __global__ void __launch_bounds__(256) k_plan_cache(const __grid_constant__ Inte
     sm1o[n] = s;
 }
 // a point's plan: from the cache when there is one, recomputed otherwise (bit-identical values)
-template <int DEG>
+template <int DEG, bool NEED_Y = true>
 __device__ __forceinline__ void cached_plan(const GridDev &g, const InterpArgs &a, int n, int &c0, int &r0, float wx[4], float wy[4], float &sm1) {
     if (a.pc_idx) {
         const int k = __ldg(a.pc_idx + n);
         c0 = k & 0xffff; r0 = k >> 16;
-        const float4 X = __ldg(a.pc_wx + n), Y = __ldg(a.pc_wy + n);
+        const float4 X = __ldg(a.pc_wx + n);
         wx[0] = X.x; wx[1] = X.y; wx[2] = X.z; wx[3] = X.w;
-        wy[0] = Y.x; wy[1] = Y.y; wy[2] = Y.z; wy[3] = Y.w;
+        if (NEED_Y) {   // (the row-separable kernel takes the y side from its row plans)
+            const float4 Y = __ldg(a.pc_wy + n);
+            wy[0] = Y.x; wy[1] = Y.y; wy[2] = Y.z; wy[3] = Y.w;
+        }
         sm1 = __ldg(a.pc_sm1 + n);
     } else {
         point_plan<DEG>(g, a.x[n], a.y[n], c0, r0, wx, wy, sm1);
