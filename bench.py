@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--levels", type=int, default=0, help="override the number of fields per step")
     ap.add_argument("--cpu-sample-levels", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra sub-records (other workloads, fp64 arm, pageable e2e)")
     ap.add_argument("--arith", type=int, default=2)
     args = ap.parse_args()
 

@@ -48,6 +48,7 @@ struct TilePlan {   // classification of the target points for the tiled kernel 
     TileDesc *d_tiles = nullptr;
     uint32_t *d_flags = nullptr;
     int *d_list = nullptr;
+    int *d_wintiles = nullptr;        // compacted list of the window kernel's tiles
     unsigned int *d_rowy = nullptr;   // row-separable tiles: y of each target row (ez_interp_rowsep.cuh)
     int nlist = 0, ntiles_fast = 0, cap = 0;
     int ntiles_rowsep = 0, vw = 0, cap_rs = 0;
@@ -107,8 +108,11 @@ struct DevBuf {
             if (p) cudaFree(p);
             p = nullptr;
             cap = 0;
-            if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return nullptr; }
-            cap = bytes;
+            // rounded up (+32 B, 256-byte granular): fields staged here end inside the allocation even after the tile kernels'
+            // 16-byte block rounding (source_blocks_inside_allocation), whatever the field length mod 4
+            const size_t want = (bytes + 32 + 255) & ~(size_t)255;
+            if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); return nullptr; }
+            cap = want;
         }
         return p;
     }
@@ -534,10 +538,19 @@ int ensure_latlon(Grid &g) {
     }
     if (ensure_device(g) < 0) return -1;
     size_t n = (size_t)g.ni * g.nj;
-    if (dev_alloc(&g.d_lat, n) < 0 || dev_alloc(&g.d_lon, n) < 0) return -1;
+    if (dev_alloc(&g.d_lat, n) < 0) { g.d_lat = nullptr; return -1; }
+    if (dev_alloc(&g.d_lon, n) < 0) { cudaFree(g.d_lat); g.d_lat = g.d_lon = nullptr; return -1; }
     ezk::calclatlon(to_dev(g), g.d_lat, g.d_lon, (int)n, S.stream);
     S.launches++;
-    CUDA_OK(cudaGetLastError());
+    // cached state shared by every session: complete before it is visible to other threads' streams
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S.stream);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "<ezb200> lat/lon build failed: %s\n", cudaGetErrorString(e));
+        cudaFree(g.d_lat); cudaFree(g.d_lon);
+        g.d_lat = g.d_lon = nullptr;
+        return -1;
+    }
     return 0;
 }
 
@@ -581,6 +594,8 @@ int point_xy(Grid &s, float lat, float lon, float *x, float *y) {
     return 0;
 }
 
+void free_gset(Gset &gs);
+
 // The gridset build: ez_calcxy (ez_calcxy.c:28) + ez_defzones (ez_defzones.c:25) for a plain source,
 // c_ezyy_calcxy (ezyy_calcxy.c:28) for a 'U' source.  Runs once per (gdout, gdin); results stay in HBM.
 Gset *ensure_gset(Grid &out, Grid &in) {
@@ -596,8 +611,13 @@ Gset *ensure_gset(Grid &out, Grid &in) {
     if (cudaMalloc((void **)&gs->d_x, n * sizeof(float)) != cudaSuccess || cudaMalloc((void **)&gs->d_y, n * sizeof(float)) != cudaSuccess ||
         cudaMalloc((void **)&gs->d_zb, n) != cudaSuccess) {
         fprintf(stderr, "<ezb200> cudaMalloc failed for the gridset (%zu points): %s\n", n, cudaGetErrorString(cudaGetLastError()));
+        free_gset(*gs);
         return nullptr;
     }
+    struct Undo {   // a failed build leaves no half-built gridset behind (and leaks nothing on retry)
+        Gset *g;
+        ~Undo() { if (g && !g->built) free_gset(*g); }
+    } undo{gs};
     unsigned int *d_counts = (unsigned int *)S.st_misc[1].get(8 * sizeof(unsigned int));
     if (!d_counts) return nullptr;
     cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned int), S.stream);
@@ -680,10 +700,15 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     const size_t ntiles = (size_t)ntx * nty;
     unsigned int *d_counters = (unsigned int *)S.st_misc[3].get(8 * sizeof(unsigned int));
     if (!d_counters) return nullptr;
+    auto free_plan = [&]() {
+        cudaFree(tp.d_tiles); cudaFree(tp.d_flags); cudaFree(tp.d_rowy); cudaFree(tp.d_list); cudaFree(tp.d_wintiles);
+        tp.d_tiles = nullptr; tp.d_flags = nullptr; tp.d_rowy = nullptr; tp.d_list = nullptr; tp.d_wintiles = nullptr;
+    };
     if (cudaMalloc((void **)&tp.d_tiles, ntiles * sizeof(TileDesc)) != cudaSuccess ||
         cudaMalloc((void **)&tp.d_flags, ntiles * 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void **)&tp.d_rowy, ntiles * 32 * sizeof(unsigned int)) != cudaSuccess) {
         fprintf(stderr, "<ezb200> cudaMalloc failed for the tile plan: %s\n", cudaGetErrorString(cudaGetLastError()));
+        free_plan();
         return nullptr;
     }
     cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), S.stream);
@@ -696,6 +721,7 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     if (cudaMemcpyAsync(hc, d_counters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
         cudaStreamSynchronize(S.stream) != cudaSuccess) {
         fprintf(stderr, "<ezb200> tile classification failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        free_plan();
         return nullptr;
     }
     tp.nlist = (int)hc[0];
@@ -706,19 +732,44 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     tp.cap_rs = (int)hc[5];   // tallest row-separable box; ezk::interp turns it into floats per staged level
     // the tile kernel pays off when most points take it (target as fine as the source); otherwise keep the per-point kernel
     tp.suitable = tp.ntiles_fast > 0 && (size_t)tp.nlist * 2 <= (size_t)a.npts;
+    if (tp.suitable && tp.ntiles_fast > tp.ntiles_rowsep) {
+        // the window kernel's tiles, compacted; both polar caps first (the rows that carry ragged work): 0, last, 1, last-1 ...
+        std::vector<TileDesc> ht(ntiles);
+        if (cudaMemcpy(ht.data(), tp.d_tiles, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost) != cudaSuccess) { free_plan(); return nullptr; }
+        std::vector<int> wt;
+        for (int b = 0; b < nty; b++) {
+            const int by = (b & 1) ? (nty - 1 - (b >> 1)) : (b >> 1);
+            for (int bx = 0; bx < ntx; bx++) {
+                const TileDesc &t = ht[(size_t)by * ntx + bx];
+                if (t.nfast > 0 && t.kind == 0) wt.push_back(by * ntx + bx);
+            }
+        }
+        if ((int)wt.size() != tp.ntiles_fast - tp.ntiles_rowsep) { fprintf(stderr, "<ezb200> tile plan: window tile count mismatch\n"); free_plan(); return nullptr; }
+        if (cudaMalloc((void **)&tp.d_wintiles, wt.size() * sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(tp.d_wintiles, wt.data(), wt.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            (void)cudaGetLastError();
+            free_plan();
+            return nullptr;
+        }
+    }
     if (tp.suitable && tp.nlist > 0) {
-        if (cudaMalloc((void **)&tp.d_list, (size_t)tp.nlist * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMalloc((void **)&tp.d_list, (size_t)tp.nlist * sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); tp.d_list = nullptr; free_plan(); return nullptr; }
         cudaMemsetAsync(d_counters, 0, sizeof(unsigned int), S.stream);
         ezk::tile_list(a, tp.d_flags, tp.d_list, d_counters, S.stream);
         S.launches++;
+        if (cudaStreamSynchronize(S.stream) != cudaSuccess) {   // the plan is shared by every session: complete before it is published
+            fprintf(stderr, "<ezb200> tile list build failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            free_plan();
+            return nullptr;
+        }
     }
-    if (!tp.suitable) {
-        cudaFree(tp.d_tiles); cudaFree(tp.d_flags); cudaFree(tp.d_rowy);
-        tp.d_tiles = nullptr; tp.d_flags = nullptr; tp.d_rowy = nullptr;
-    }
+    if (!tp.suitable) free_plan();
     if (S.opt.verbose > 0)
-        fprintf(stderr, "<ezb200> tile plan: %d of %d points on the per-point list, %d of %zu tiles active (%d row-separable), %s\n", tp.nlist,
-                a.npts, tp.ntiles_fast, ntiles, tp.ntiles_rowsep, tp.suitable ? "tiled kernels" : "per-point kernel");
+        fprintf(stderr, "<ezb200> tile plan: %d of %d points on the per-point list, %d of %zu tiles active (%d row-separable), %s; window tiles: "
+                "%.2f shared-memory wavefronts per LDS at the chosen pitch (%.2f at the minimal pitch), %d floats per staged level\n", tp.nlist,
+                a.npts, tp.ntiles_fast, ntiles, tp.ntiles_rowsep, tp.suitable ? "tiled kernels" : "per-point kernel",
+                hc[6] / (8.0 * (tp.ntiles_fast - tp.ntiles_rowsep > 0 ? tp.ntiles_fast - tp.ntiles_rowsep : 1)),
+                hc[7] / (8.0 * (tp.ntiles_fast - tp.ntiles_rowsep > 0 ? tp.ntiles_fast - tp.ntiles_rowsep : 1)), tp.cap);
     tp.built = true;
     return &tp;
 }
@@ -734,6 +785,7 @@ void ensure_plan_cache(TilePlan &tp, const InterpArgs &a) {
             cudaMalloc((void **)&tp.d_pc_wy, n * sizeof(float4)) == cudaSuccess && cudaMalloc((void **)&tp.d_pc_sm1, n * sizeof(float)) == cudaSuccess) {
             ezk::plan_cache(a, tp.d_pc_idx, tp.d_pc_wx, tp.d_pc_wy, tp.d_pc_sm1, S.stream);
             S.launches++;
+            (void)cudaStreamSynchronize(S.stream);   // shared by every session: complete before other streams may read it
         } else {   // not enough memory: the tile kernels recompute the plans
             (void)cudaGetLastError();
             cudaFree(tp.d_pc_idx); cudaFree(tp.d_pc_wx); cudaFree(tp.d_pc_wy); cudaFree(tp.d_pc_sm1);
@@ -747,6 +799,7 @@ void free_gset(Gset &gs) {
         if (tp.d_tiles) cudaFree(tp.d_tiles);
         if (tp.d_flags) cudaFree(tp.d_flags);
         if (tp.d_list) cudaFree(tp.d_list);
+        if (tp.d_wintiles) cudaFree(tp.d_wintiles);
         if (tp.d_rowy) cudaFree(tp.d_rowy);
         if (tp.d_pc_idx) cudaFree(tp.d_pc_idx);
         if (tp.d_pc_wx) cudaFree(tp.d_pc_wx);
@@ -895,6 +948,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.tile_cap_rs = tp->cap_rs;
             a.ntiles_rowsep = tp->ntiles_rowsep;
             a.ntiles_window = tp->ntiles_fast - tp->ntiles_rowsep;
+            a.win_tiles = tp->d_wintiles;
             a.list = tp->d_list;
             a.nlist = tp->nlist;
         }

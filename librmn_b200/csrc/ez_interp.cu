@@ -724,6 +724,10 @@ bool tiled_eligible(const InterpArgs &a) {
     if (a.out_ni < 2 || a.out_nj < 2) return false;
     if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
     if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
+    // the tile kernels address a pipeline stage (LPS consecutive fields) through signed 32-bit byte offsets
+    const long field = a.yy ? 2 * a.panel_stride : (long)a.src.ni * (a.src.j2 - a.src.j1 + 1);
+    const long span = (long)LPS * (a.in_stride < 0 ? -a.in_stride : a.in_stride) + field;
+    if (span * 4 >= (1L << 31)) return false;
     return true;
 }
 
@@ -760,7 +764,11 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         int ntx, nty, launches = 0;
         tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
         dim3 grid(ntx, nty);
-        const size_t smem = (size_t)NSTAGE * LPS * a.tile_cap * sizeof(float);
+        static const size_t smem_pad = getenv("EZB200_WIN_SMEM_PAD") ? (size_t)atol(getenv("EZB200_WIN_SMEM_PAD")) : 0;   // occupancy experiments
+        const size_t smem = (size_t)NSTAGE * LPS * a.tile_cap * sizeof(float) + smem_pad;
+        // the window kernel: one CTA per tile of the compacted list
+        const int win_ctas = a.ntiles_window;
+        const dim3 grid_win(win_ctas > 0 ? win_ctas : 1);
         // row-separable kernel: staged pitch congruent to the source row length mod 4 (16-byte cp.async, ez_interp_rowsep.cuh)
         const int rs_p = rs_pitch(a.src.ni);
         InterpArgs ar = a;
@@ -768,7 +776,7 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         const size_t smem_rs = (size_t)RS_NSTAGE * LPS * ar.tile_cap_rs * sizeof(float) + 2 * (size_t)TO * RS_VP * sizeof(float4) + TO * sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
-            const int mx = NSTAGE * LPS * TILE_CAP * (int)sizeof(float);
+            const int mx = 227 * 1024;
             cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             const int mxr = RS_NSTAGE * LPS * (TILE_CAP + 16) * (int)sizeof(float) + 2 * TO * RS_VP * (int)sizeof(float4) + TO * (int)sizeof(double);
@@ -791,8 +799,8 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         }
         if (timing) cudaEventRecord(timing->ev[0], s);
         if (a.ntiles_window > 0 && conc) {   // the largest kernel first
-            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_WIN, smem, s>>>(a);
-            else k_interp_tiled<1><<<grid, NTHR_WIN, smem, s>>>(a);
+            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
+            else k_interp_tiled<1><<<grid_win, NTHR_WIN, smem, s>>>(a);
             launches++;
         }
         if (a.ntiles_rowsep > 0) {
@@ -808,8 +816,8 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         }
         if (timing) cudaEventRecord(timing->ev[1], s);
         if (a.ntiles_window > 0 && !conc) {
-            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid, NTHR_WIN, smem, s>>>(a);
-            else k_interp_tiled<1><<<grid, NTHR_WIN, smem, s>>>(a);
+            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
+            else k_interp_tiled<1><<<grid_win, NTHR_WIN, smem, s>>>(a);
             launches++;
         }
         if (timing) cudaEventRecord(timing->ev[2], s);

@@ -1,5 +1,5 @@
 // librmn_b200/csrc/ez_interp_rowsep.cuh -- the row-separable tile kernel (linear and cubic, "arith = 2").
-// Included by ez_interp.cu after ez_interp_tiled.cuh (shares its tile geometry, classification and producer warp).
+// Included by ez_interp.cu after ez_interp_tiled.cuh (shares its tile geometry and classification).
 //
 // Why: when the target rows run along the source grid's y axis -- lat-lon targets fed from lat-lon, Gaussian or
 // unrotated/identity-rotated Z grids: BASELINE.json's C5 and the Yin half of C2 -- every point of a target row
@@ -44,12 +44,6 @@ __host__ __device__ constexpr int rs_pitch(int ni) { return 35 + (((ni - 35) % 4
 __host__ __device__ constexpr int rs_cap(int P, int h) { return (P * h + 8 + 3) & ~3; }
 
 __device__ __forceinline__ void compute_barrier() { __syncthreads(); }
-// shared memory through 32-bit shared-window addresses (keeps address arithmetic to one IADD per access group)
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -65,27 +59,6 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
 __device__ __forceinline__ void sts_f32x4(uint32_t addr, float2 lo, float2 hi) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y) : "memory");
 }
-// mbarrier + 1-D bulk copy (TMA) primitives
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "RS_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra RS_DONE;\n\t"
-        "bra RS_WAIT;\n\t"
-        "RS_DONE:\n\t"
-        "}" ::"r"(mbar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-
 __device__ __forceinline__ float robust_ref(float z) { return (fabsf(z) < 1e15f) ? z : 0.f; }
 
 static_assert(LPS == 4, "the row-separable kernel processes one 4-level pipeline stage per pass");

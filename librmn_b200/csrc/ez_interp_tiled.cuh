@@ -5,17 +5,24 @@
 // ~2.5 L1 wavefronts per gather and 61 % of the L1 wavefront rate while HBM sits at 8 % (profiles/r1a_*).
 // The L1/LSU path, not HBM, is the wall.  This kernel removes most of that traffic:
 //   * a CTA owns a 32 x 32 tile of TARGET points; the bounding box of all their stencils in the source
-//     level (a few KB: the tile's footprint) is staged in shared memory by cp.async, double-buffered
-//     across levels, so global memory is read in whole rows (coalesced) exactly once per tile and level;
+//     level (a few KB: the tile's footprint) is staged in shared memory by 16-byte cp.async, NSTAGE stages of
+//     LPS levels deep, so global memory is read in whole rows (coalesced) exactly once per tile and level;
 //   * a thread owns a 2 x 2 block of target points.  When the target grid is as fine as or finer than the
-//     source (every configuration of BASELINE.json), the four 4x4 stencils fit one 5 x 5 window: 25
-//     conflict-free LDS feed 4 outputs (6.25 loads per output instead of 16).  Each output applies its
-//     own weights zero-padded to the window (wx'[5], wy'[5]); no selects, no dynamic register indexing;
+//     source (every configuration of BASELINE.json), the four 4x4 stencils fit one 5 x 5 window: 25 LDS feed
+//     4 outputs (6.25 loads per output instead of 16).  Each output applies its own weights zero-padded to the
+//     window (wx'[5], wy'[5]); no selects, no dynamic register indexing;
 //   * the arithmetic is the fp32 difference form of ez_interp_fast.cuh taken about the window centre:
-//     zo = zc (1 + s) + sum_r wy'_r sum_c wx'_c (z_rc - zc), weights from the fp64 plan.
+//     zo = zc (1 + s) + sum_r wy'_r sum_c wx'_c (z_rc - zc), weights from the fp64 plan, evaluated on packed
+//     fp32x2 instructions whose two halves are two consecutive LEVELS of one point (the weight is the scalar
+//     broadcast operand): FADD2 forms the differences, FFMA2 the sums;
+//   * the staged row pitch is chosen per tile (k_tile_classify) among the values congruent to the source row
+//     length mod 4 (what the 16-byte copies need) so as to minimise shared-memory bank conflicts of the tile's
+//     own warps: on a rotated panel the 32 window origins of a warp are a sheared lattice, and the pitch decides
+//     which of them collide (scripts/analysis/bank_sim.py: 2.0 wavefronts per LDS at the minimal pitch, 1.4 at
+//     the best of 8).
 // Points that do not fit (zone points, the longitudinal seam, Yin/Yang panel borders, windows larger than
-// 5 x 5) are classified ONCE per (gridset, degree) by k_tile_classify into a compacted list and handled by
-// the per-point kernel (k_interp_fast with an index list); the tile kernel never branches on them.
+// 5 x 5 or overhanging the field) are classified ONCE per (gridset, degree) by k_tile_classify into a compacted
+// list and handled by the per-point kernel (k_interp_fast with an index list); the tile kernel never branches on them.
 #pragma once
 #include <cuda_pipeline_primitives.h>
 
@@ -35,21 +42,35 @@ constexpr int TO = 2 * TT;         // target points per tile side
 #ifndef EZ_TILED_MINB
 #define EZ_TILED_MINB 2
 #endif
-#ifndef EZ_TILED_UNROLL
-#define EZ_TILED_UNROLL 1
+#ifndef EZ_WIN_NPITCH
+#define EZ_WIN_NPITCH 8
 #endif
-constexpr int TILED_UNROLL = EZ_TILED_UNROLL;
-#ifndef EZ_TILED_NOPROD
-#define EZ_TILED_NOPROD 1
+#ifndef EZ_WIN_CAPLIM
+#define EZ_WIN_CAPLIM 2304
 #endif
-// EZ_TILED_NOPROD: the window kernel stages with 16-byte cp.async issued by all its threads through a staging pitch
-// congruent to the source row length mod 4 (see ez_interp_rowsep.cuh), no producer warp, one barrier per stage.
-constexpr bool TILED_NOPROD = EZ_TILED_NOPROD != 0;
-__host__ __device__ constexpr int win_pitch(int w, int ni) { return (w + 3) + ((((ni - (w + 3)) % 4) + 4) % 4); }
-__host__ __device__ constexpr int win_cap(int w, int h) { return TILED_NOPROD ? (w + 6) * h + 8 : (w | 1) * h; }   // levels of a stage evaluated per loop iteration in the window kernel
-constexpr int TILE_CAP = EZ_TILE_CAP;     // floats per shared-memory buffer
+constexpr int TILE_CAP = EZ_TILE_CAP;     // floats per staged level a tile box may take at most
 constexpr int LPS = EZ_LPS;               // source levels per pipeline stage (one CTA barrier per stage)
-constexpr int NSTAGE = EZ_NSTAGE;          // buffers per CTA: the producer warp runs NSTAGE-1 source levels ahead of the compute warps
+constexpr int NSTAGE = EZ_NSTAGE;         // stages in flight per CTA
+constexpr int NTHR_WIN = TT * TT;
+constexpr int WIN_NPITCH = EZ_WIN_NPITCH; // candidate pitches per tile: win_pitch(w, ni) + 4 j, j < WIN_NPITCH
+constexpr int WIN_CAPLIM = EZ_WIN_CAPLIM; // a wider-than-minimal pitch is only taken while the staged level stays below this (2 CTAs/SM)
+// smallest staging pitch >= w + 3 congruent to the source row length mod 4: a 16-byte aligned chunk of a source row is
+// then 16-byte aligned in shared memory for every row of the box (see ez_interp_rowsep.cuh)
+__host__ __device__ constexpr int win_pitch(int w, int ni) { return (w + 3) + ((((ni - (w + 3)) % 4) + 4) % 4); }
+__host__ __device__ constexpr int win_cap(int pitch, int h) { return pitch * h + 8; }
+
+// shared memory through 32-bit shared-window addresses (keeps address arithmetic to one IADD per access group)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32_imm(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
 
 template <int DEG> struct Sten {
     static constexpr int S = (DEG == 3) ? 4 : 2;   // stencil width
@@ -136,7 +157,10 @@ __device__ __forceinline__ QuadClass classify_thread(const GridDev &g, const Int
         rrow[row] = r0;
     }
     k.elig = ok && nvalid > 0;
-    k.fast = k.elig && (k.cmax - k.cmin) <= 1 && (k.rmax - k.rmin) <= 1;
+    // the window kernel reads the whole W x W window: it must lie inside the field (the zero-weight overhang column/row
+    // would otherwise read the next row's first element or past the end of the last field)
+    constexpr int W = Sten<DEG>::W;
+    k.fast = k.elig && (k.cmax - k.cmin) <= 1 && (k.rmax - k.rmin) <= 1 && (k.cmin + W) <= g.ni && (k.rmin + W) <= (g.j2 - g.j1 + 1);
     k.rowpair = k.elig && ysame && (!(k.yok[0] && k.yok[1]) || abs(rrow[1] - rrow[0]) <= 1);
     return k;
 }
@@ -151,12 +175,14 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     __shared__ int s_cnt[2];
     __shared__ unsigned int s_rowy[TO];
     __shared__ int s_bad;             // some quad breaks the row-separable structure
+    __shared__ int s_conf[WIN_NPITCH];   // window kernel: shared-memory wavefronts per LDS summed over the tile's warps, per candidate pitch
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const Quad q = quad_of_thread(blockIdx.x, blockIdx.y);
     const int ni = a.out_ni, nj = a.out_nj;
     if (threadIdx.x < 8) s_box[threadIdx.x] = (threadIdx.x & 2) ? INT_MIN : INT_MAX;
     if (threadIdx.x < TO) s_rowy[threadIdx.x] = ROWY_NONE;
     if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_bad = 0; }
+    if (threadIdx.x < WIN_NPITCH) s_conf[threadIdx.x] = 0;
     // panel of the tile: majority of the threads' first points
     const bool v0 = q.valid(0, ni, nj);
     const bool yang0 = v0 && a.yy && a.zb && (a.zb[q.index(0, ni)] & ZB_YANG);
@@ -190,14 +216,27 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     const bool rowsep = a.rowsep_enable && !s_bad && sc0 != INT_MAX && sw <= 32 && sh <= 51 && 38L * sh + 8 <= TILE_CAP;
     const int c0 = rowsep ? sc0 : s_box[0], r0 = rowsep ? sr0 : s_box[1];
     const int c1 = rowsep ? s_box[6] : s_box[2], r1 = rowsep ? s_box[7] : s_box[3];
-    // the box holds every fast thread's full window; a window may overhang the field by one column/row on the
-    // high side (that column/row carries zero weights) -- stage_tile replicates the field edge there
     const int w = c1 - c0 + 1, h = r1 - r0 + 1;
-    const bool box_ok = (c0 != INT_MAX) && w <= 64 && (long)win_cap(w, h) <= TILE_CAP && (!TILED_NOPROD || rowsep || h * ((w + 6) >> 2) <= 2 * TT * TT);
+    const int pmin = win_pitch(w, tile_panel ? a.src2.ni : a.src.ni);
+    const bool box_ok = (c0 != INT_MAX) && w <= 64 && (rowsep || ((long)win_cap(pmin, h) <= TILE_CAP && h * ((w + 6) >> 2) <= 2 * TT * TT));
     const bool fast = (rowsep ? k.elig : k.fast) && box_ok;
     const unsigned int ballot = __ballot_sync(0xffffffffu, fast);
     if ((threadIdx.x & 31) == 0) flags[tile * 8 + (threadIdx.x >> 5)] = ballot;
     if (threadIdx.x < TO) rowy[tile * TO + threadIdx.x] = rowsep ? s_rowy[threadIdx.x] : ROWY_NONE;
+    // window tiles: bank conflicts of this warp's LDS for every candidate pitch (lanes = the threads that will load)
+    if (!rowsep && box_ok) {
+        const int lane = threadIdx.x & 31;
+        const int bc = k.cmin - c0, br = k.rmin - r0;
+#pragma unroll 1
+        for (int j = 0; j < WIN_NPITCH; j++) {
+            const int addr = br * (pmin + 4 * j) + bc;
+            const unsigned int mb = __match_any_sync(0xffffffffu, fast ? (addr & 31) : (32 + lane));
+            const unsigned int ma = __match_any_sync(0xffffffffu, fast ? addr : (-1 - lane));
+            const unsigned int leaders = __ballot_sync(0xffffffffu, fast && lane == (__ffs(ma) - 1));
+            const int m = __reduce_max_sync(0xffffffffu, fast ? __popc(mb & leaders) : 0);
+            if (lane == 0) atomicAdd(&s_conf[j], m);
+        }
+    }
     int nslow = 0;
     if (!fast)
         for (int p = 0; p < 4; p++) nslow += q.valid(p, ni, nj) ? 1 : 0;
@@ -207,10 +246,19 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
     if (threadIdx.x == 0) {
         TileDesc td;
         td.c0 = box_ok ? c0 : 0; td.r0 = box_ok ? r0 : 0; td.w = box_ok ? w : 0; td.h = box_ok ? h : 0;
-        td.panel = tile_panel; td.nfast = s_cnt[1]; td.nslow = s_cnt[0]; td.kind = (rowsep && box_ok) ? 1 : 0;
+        td.panel = tile_panel; td.nfast = s_cnt[1]; td.kind = (rowsep && box_ok) ? 1 : 0;
+        int best = 0;
+        if (box_ok && !rowsep)
+            for (int j = 1; j < WIN_NPITCH; j++)
+                if (win_cap(pmin + 4 * j, h) <= WIN_CAPLIM && s_conf[j] < s_conf[best]) best = j;
+        td.pitch = box_ok ? pmin + 4 * best : 0;
         tiles[tile] = td;
         atomicAdd(counters + 0, (unsigned int)s_cnt[0]);
-        if (box_ok && s_cnt[1] > 0 && td.kind == 0) atomicMax(counters + 2, (unsigned int)win_cap(w, h));
+        if (box_ok && s_cnt[1] > 0 && td.kind == 0) {
+            atomicMax(counters + 2, (unsigned int)win_cap(td.pitch, h));
+            atomicAdd(counters + 6, (unsigned int)s_conf[best]);     // diagnostics: wavefronts per LDS, summed over warps, chosen
+            atomicAdd(counters + 7, (unsigned int)s_conf[0]);        // ... and at the minimal pitch
+        }
         if (s_cnt[1] > 0) atomicAdd(counters + 1, 1u);
         if (td.kind == 1 && s_cnt[1] > 0) {
             atomicMax(counters + 3, (unsigned int)w);
@@ -282,273 +330,135 @@ __device__ __forceinline__ void cached_plan(const GridDev &g, const InterpArgs &
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the tile kernel
+// the window tile kernel
 // ---------------------------------------------------------------------------------------------------
-// CTA-wide barrier shared by the producer warp and the compute warps (they reach it from different code paths)
-#ifndef EZ_NPROD
-#define EZ_NPROD 1
-#endif
-constexpr int NPROD = EZ_NPROD;           // producer warps per CTA (each has its own limit of outstanding cp.async requests)
-constexpr int NTHR_TILED = TT * TT + 32 * NPROD;
-template <int NTHR_BAR = NTHR_TILED>
-__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NTHR_BAR) : "memory"); }
-
-// The producer warp: stages the tile's box of every source level into shared memory with cp.async (LDGSTS), one
-// level ahead of the compute warps.  Lane l copies box columns l and l+32 (boxes are at most 64 wide) of every box
-// row; per row that is two predicated 4-byte copies and two pointer bumps.  Box cells that overhang the field (a
-// window may stick out by one zero-weight row/column on the high side) are never written and keep the zero fill.
-__device__ __forceinline__ void stage_rows(float *__restrict__ dst, const float *__restrict__ src, int nrow, int src_ni, int pitch, bool c0ok,
-                                           bool c1ok) {
-#pragma unroll 4
-    for (int r = 0; r < nrow; r++) {
-        if (c0ok) __pipeline_memcpy_async(dst, src, 4);
-        if (c1ok) __pipeline_memcpy_async(dst + 32, src + 32, 4);
-        src += src_ni;
-        dst += pitch;
-    }
-}
-
-template <int NTHR_BAR = NTHR_TILED>
-__device__ __forceinline__ void producer_warp(const InterpArgs &a, const float *__restrict__ zin, const TileDesc &td, int src_ni, int src_rows,
-                                              float *__restrict__ smem, const int pitch, const int cap) {
-    const int lane = threadIdx.x & 31;
-    const int pw = (threadIdx.x - (NTHR_BAR - 32 * NPROD)) >> 5;    // this producer warp copies box rows pw, pw + NPROD, ...
-    const int nrow = (min(td.h, src_rows - td.r0) - pw + NPROD - 1) / NPROD;
-    const bool c0ok = lane < td.w && (td.c0 + lane) < src_ni;
-    const bool c1ok = (lane + 32) < td.w && (td.c0 + lane + 32) < src_ni;
-    const float *src = zin + (long)(td.r0 + pw) * src_ni + td.c0 + lane;
-    const int nf = a.nfields;
-    const long is = a.in_stride;
-    // A stage holds LPS consecutive levels; the producer runs NSTAGE-1 stages ahead.  Empty commit groups keep the
-    // group count uniform at the tail.
-    const int nstages = (nf + LPS - 1) / LPS;
-    auto stage = [&](int st) {
-        if (st < nstages) {
-            float *dst = smem + (st % NSTAGE) * LPS * cap + pw * pitch + lane;
-#pragma unroll 1
-            for (int l = 0; l < LPS; l++) {
-                const int f = st * LPS + l;
-                if (f < nf) stage_rows(dst + l * cap, src + f * is, nrow, NPROD * src_ni, NPROD * pitch, c0ok, c1ok);
-            }
-        }
-        __pipeline_commit();
-    };
-#pragma unroll
-    for (int k = 0; k < NSTAGE - 1; k++) stage(k);
-    for (int st = 0; st < nstages; st++) {
-        __pipeline_wait_prior(NSTAGE - 2);   // stage st has landed
-        tile_barrier<NTHR_BAR>();            // ... and every compute warp is done with stage st-1, whose buffers are refilled next
-        stage(st + NSTAGE - 1);
-    }
-}
-
-// The compute warps.  Arithmetic of one level for one thread (2 x 2 target points p0 p1 / p2 p3, W x W window):
-//   d_rc = z_rc - zc                                  (zc = window centre; fp32 difference form)
-//   out_p = zc (1 + s_p) + sum_r wy_p[r] * ( sum_c wx_p[c] * d_rc )
-// evaluated with packed fp32x2 instructions (FFMA2/FMUL2: sm_100 issues two fp32 FMAs per instruction, measured
-// 114 vs 72 FMA/clk/SM for scalar FFMA, scripts/ubench/ffma2.cu): the two points of a row pair share the data
-// operand (d, d) and carry their own weights in the two halves.  The window is streamed row by row, so only one
-// row of data is live in registers.
+// Arithmetic of one level PAIR (levels A, B of a pipeline stage) for one thread (2 x 2 target points, W x W window):
+//   d_rc = (zA_rc - zcA, zB_rc - zcB)                      FADD2 ; zc = window centre of the level (fp32 difference form)
+//   out_p = zc (1 + s_p) + sum_r wy_p[r] * ( sum_c wx_p[c] * d_rc )     FFMA2, the weight is the scalar broadcast operand
+// The window is streamed row by row, so only one row of data (W register pairs) is live.
 template <int DEG>
-__device__ __forceinline__ void compute_warps(const GridDev &g, const InterpArgs &a, const TileDesc &td, const Quad &q, bool fast,
-                                              const float *__restrict__ smem) {
-    constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
-    const int ni = a.out_ni, nj = a.out_nj;
-    const int pitch = td.w | 1;
-    float2 wxp[2][W], wyp[2][W], smp[2];   // [pair][k] = (weight of point 2*pair, weight of point 2*pair+1)
-    bool valid[4] = {false, false, false, false};
-    int base = 0;
-    if (fast) {
-        int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
-        float tx[4][4], ty[4][4], sm1[4];
+struct WinThread {
+    static constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
+    float wx[4][W], wy[4][W], sm1[4];   // per point, zero padded to the window
+    uint32_t roff[W];                   // byte offset of window row r from window element (0, 0)
+};
+
+template <int DEG, bool HASB>
+__device__ __forceinline__ void window_pair(const WinThread<DEG> &t, uint32_t aA, uint32_t aB, float *__restrict__ w0, int ni, long os,
+                                            bool full, const bool (&valid)[4]) {
+    constexpr int W = Sten<DEG>::W;
+    constexpr int CTR = (W / 2) * 4;
+    const float2 zc = make_float2(lds_f32_imm<CTR>(aA + t.roff[W / 2]), lds_f32_imm<CTR>(aB + t.roff[W / 2]));
+    const float2 nzc = make_float2(-zc.x, -zc.y);
+    float2 acc[4];
+#pragma unroll
+    for (int r = 0; r < W; r++) {
+        const uint32_t ar = aA + t.roff[r], br = aB + t.roff[r];
+        float2 d[W];
+        d[0] = __fadd2_rn(make_float2(lds_f32_imm<0>(ar), lds_f32_imm<0>(br)), nzc);
+        d[1] = __fadd2_rn(make_float2(lds_f32_imm<4>(ar), lds_f32_imm<4>(br)), nzc);
+        d[2] = __fadd2_rn(make_float2(lds_f32_imm<8>(ar), lds_f32_imm<8>(br)), nzc);
+        if (W > 3) {
+            d[3] = __fadd2_rn(make_float2(lds_f32_imm<12>(ar), lds_f32_imm<12>(br)), nzc);
+            d[W - 1] = __fadd2_rn(make_float2(lds_f32_imm<4 * (W - 1)>(ar), lds_f32_imm<4 * (W - 1)>(br)), nzc);
+        }
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            valid[p] = q.valid(p, ni, nj);
-            c0[p] = INT_MAX; r0[p] = INT_MAX; sm1[p] = 0.f;
-            if (valid[p]) {
-                const int n = q.index(p, ni);
-                point_plan<DEG>(g, a.x[n], a.y[n], c0[p], r0[p], tx[p], ty[p], sm1[p]);
-                wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
-            }
+            float2 rs = __fmul2_rn(make_float2(t.wx[p][0], t.wx[p][0]), d[0]);
+#pragma unroll
+            for (int c = 1; c < W; c++) rs = __ffma2_rn(make_float2(t.wx[p][c], t.wx[p][c]), d[c], rs);
+            const float2 wyr = make_float2(t.wy[p][r], t.wy[p][r]);
+            acc[p] = (r == 0) ? __fmul2_rn(wyr, rs) : __ffma2_rn(wyr, rs, acc[p]);
         }
-        float wx[4][W], wy[4][W];
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const bool sx = valid[p] && (c0[p] != wc0), sy = valid[p] && (r0[p] != wr0);   // offset 0 or 1 inside the window
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                const float lo = (k < S) ? tx[p][k] : 0.f, hi = (k > 0) ? tx[p][k - 1] : 0.f;
-                wx[p][k] = valid[p] ? (sx ? hi : lo) : 0.f;
-                const float lo2 = (k < S) ? ty[p][k] : 0.f, hi2 = (k > 0) ? ty[p][k - 1] : 0.f;
-                wy[p][k] = valid[p] ? (sy ? hi2 : lo2) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int pp = 0; pp < 2; pp++) {
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                wxp[pp][k] = make_float2(wx[2 * pp][k], wx[2 * pp + 1][k]);
-                wyp[pp][k] = make_float2(wy[2 * pp][k], wy[2 * pp + 1][k]);
-            }
-            smp[pp] = make_float2(sm1[2 * pp], sm1[2 * pp + 1]);
-        }
-        base = (wr0 - td.r0) * pitch + (wc0 - td.c0);
     }
-    const int nf = a.nfields;
-    const long os = a.out_stride;
-    // float2 stores need all four points and 8-byte alignment (even target row length; q.ox is even)
-    const bool full = fast && ((ni & 1) == 0) && valid[3] && ((reinterpret_cast<uintptr_t>(a.zout) & 7) == 0) && ((os & 1) == 0);
-    float *w0 = a.zout + (long)q.oy * ni + q.ox;
-    const int cap = a.tile_cap;
-    const int nstages = (nf + LPS - 1) / LPS;
-    for (int st = 0; st < nstages; st++) {
-        tile_barrier();
-        const float *sbase = smem + (st % NSTAGE) * LPS * cap + base;
-        const int nl = min(LPS, nf - st * LPS);
-        if (fast) {
-#pragma unroll TILED_UNROLL
-            for (int l = 0; l < nl; l++) {
-                const float *s = sbase + l * cap;
-                const float zc = s[(W / 2) * pitch + W / 2];
-                const float2 zc2 = make_float2(zc, zc);
-                float2 acc[2];
+    float2 res[4];
 #pragma unroll
-                for (int r = 0; r < W; r++) {
-                    float2 d[W];
-#pragma unroll
-                    for (int c = 0; c < W; c++) {
-                        const float v = s[r * pitch + c] - zc;
-                        d[c] = make_float2(v, v);
-                    }
-#pragma unroll
-                    for (int pp = 0; pp < 2; pp++) {
-                        float2 rs = __fmul2_rn(wxp[pp][0], d[0]);
-#pragma unroll
-                        for (int c = 1; c < W; c++) rs = __ffma2_rn(wxp[pp][c], d[c], rs);
-                        acc[pp] = (r == 0) ? __fmul2_rn(wyp[pp][0], rs) : __ffma2_rn(wyp[pp][r], rs, acc[pp]);
-                    }
-                }
-                const float2 r01 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[0], acc[0]));
-                const float2 r23 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[1], acc[1]));
-                float *w1 = w0 + ni;
-                if (full) {
-                    *reinterpret_cast<float2 *>(w0) = r01;
-                    *reinterpret_cast<float2 *>(w1) = r23;
-                } else {
-                    if (valid[0]) w0[0] = r01.x;
-                    if (valid[1]) w0[1] = r01.y;
-                    if (valid[2]) w1[0] = r23.x;
-                    if (valid[3]) w1[1] = r23.y;
-                }
-                w0 += os;
-            }
+    for (int p = 0; p < 4; p++) res[p] = __fadd2_rn(zc, __ffma2_rn(zc, make_float2(t.sm1[p], t.sm1[p]), acc[p]));
+    float *w1 = w0 + ni;
+    if (full) {
+        *reinterpret_cast<float2 *>(w0) = make_float2(res[0].x, res[1].x);
+        *reinterpret_cast<float2 *>(w1) = make_float2(res[2].x, res[3].x);
+        if (HASB) {
+            *reinterpret_cast<float2 *>(w0 + os) = make_float2(res[0].y, res[1].y);
+            *reinterpret_cast<float2 *>(w1 + os) = make_float2(res[2].y, res[3].y);
+        }
+    } else {
+        if (valid[0]) w0[0] = res[0].x;
+        if (valid[1]) w0[1] = res[1].x;
+        if (valid[2]) w1[0] = res[2].x;
+        if (valid[3]) w1[1] = res[3].x;
+        if (HASB) {
+            if (valid[0]) w0[os] = res[0].y;
+            if (valid[1]) w0[os + 1] = res[1].y;
+            if (valid[2]) w1[os] = res[2].y;
+            if (valid[3]) w1[os + 1] = res[3].y;
         }
     }
 }
-
-// ---------------------------------------------------------------------------------------------------
-// EZ_TILED_NOPROD variant: same arithmetic, staging by every thread (16-byte cp.async), one barrier per stage
-// ---------------------------------------------------------------------------------------------------
-constexpr int NTHR_WIN = TILED_NOPROD ? TT * TT : NTHR_TILED;
 
 template <int DEG>
-__device__ __forceinline__ void window_all(const GridDev &g, const InterpArgs &a, const TileDesc &td, const Quad &q, bool fast,
-                                           const float *__restrict__ zin, int src_rows, float *__restrict__ smem) {
+__device__ __forceinline__ void window_tile(const GridDev &g, const InterpArgs &a, const TileDesc &td, const Quad &q, bool fast,
+                                            const float *__restrict__ zin, int src_rows, const uint32_t smem32) {
     constexpr int S = Sten<DEG>::S, W = Sten<DEG>::W;
     const int ni = a.out_ni, nj = a.out_nj;
-    const int pitch = win_pitch(td.w, g.ni);
-    float2 wxp[2][W], wyp[2][W], smp[2];   // [pair][k] = (weight of point 2*pair, weight of point 2*pair+1)
-    bool valid[4] = {false, false, false, false};
-    int base = 0;
-    if (fast) {
-        int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
-        float tx[4][4], ty[4][4], sm1[4];
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            valid[p] = q.valid(p, ni, nj);
-            c0[p] = INT_MAX; r0[p] = INT_MAX; sm1[p] = 0.f;
-            if (valid[p]) {
-                const int n = q.index(p, ni);
-                cached_plan<DEG>(g, a, n, c0[p], r0[p], tx[p], ty[p], sm1[p]);
-                wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
-            }
-        }
-        float wx[4][W], wy[4][W];
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const bool sx = valid[p] && (c0[p] != wc0), sy = valid[p] && (r0[p] != wr0);   // offset 0 or 1 inside the window
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                const float lo = (k < S) ? tx[p][k] : 0.f, hi = (k > 0) ? tx[p][k - 1] : 0.f;
-                wx[p][k] = valid[p] ? (sx ? hi : lo) : 0.f;
-                const float lo2 = (k < S) ? ty[p][k] : 0.f, hi2 = (k > 0) ? ty[p][k - 1] : 0.f;
-                wy[p][k] = valid[p] ? (sy ? hi2 : lo2) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int pp = 0; pp < 2; pp++) {
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                wxp[pp][k] = make_float2(wx[2 * pp][k], wx[2 * pp + 1][k]);
-                wyp[pp][k] = make_float2(wy[2 * pp][k], wy[2 * pp + 1][k]);
-            }
-            smp[pp] = make_float2(sm1[2 * pp], sm1[2 * pp + 1]);
-        }
-        base = (wr0 - td.r0) * pitch + (wc0 - td.c0);
-    }
+    const int pitch = td.pitch;
     const int nf = a.nfields;
     const long os = a.out_stride, is = a.in_stride;
-    // float2 stores need all four points and 8-byte alignment (even target row length; q.ox is even)
-    const bool full = fast && ((ni & 1) == 0) && valid[3] && ((reinterpret_cast<uintptr_t>(a.zout) & 7) == 0) && ((os & 1) == 0);
-    float *w0 = a.zout + (long)q.oy * ni + q.ox;
-    const int cap = a.tile_cap;
+    const uint32_t capB = (uint32_t)a.tile_cap * 4u;
     const int nstages = (nf + LPS - 1) / LPS;
 
-    // ---- copy side (see ez_interp_rowsep.cuh): box element (r, j) of level l of a stage at float offset delta_l + r pitch + j
-    // of the level's buffer, delta_l = (float index in memory of source element (r0, c0)) mod 4; thread t copies chunks t and
-    // t + 256 of each level (chunk = row t / nck, 16-byte chunk t % nck of that row).
-    const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t capB = (uint32_t)cap * 4u;
+    // ---- copy side (see ez_interp_rowsep.cuh): box element (r, j) of level l of a stage sits at float offset
+    // delta_l + r pitch + j of the level's buffer, delta_l = (float index in memory of source element (r0, c0) of that level) mod 4.
+    // With pitch == ni (mod 4) every 16-byte aligned chunk of a source row is 16-byte aligned in shared memory.  delta depends on
+    // the level only through l = f mod 4 (LPS == 4), so a thread's offsets are computed once.  Thread t copies chunks t and
+    // t + 256 of each level (chunk = box row t / nck, 16-byte chunk t % nck of that row): chunk k of row `crow` starts at box
+    // column 4 k - phi, phi = (delta_l + crow pitch) mod 4.
     const int nrow = min(td.h, src_rows - td.r0);
     const int nck = (td.w + 6) >> 2;
-    unsigned int dpk = 0u;
-    int cj[2] = {0, 0}, crowoff[2] = {0, 0};
-    unsigned int cvalid = 0u;     // bit 4 k + l: slot k, level l
-    uint32_t cbase[2] = {0u, 0u};
+    unsigned int dpk = 0u;          // 2 bits per level: delta_l
     {
         const float *lvl0 = zin + (long)td.r0 * g.ni + td.c0;
 #pragma unroll
         for (int l = 0; l < LPS; l++) dpk |= (unsigned int)((reinterpret_cast<uintptr_t>(lvl0 + l * is) >> 2) & 3u) << (2 * l);
+    }
+    // slot 0 (every thread): byte offsets of the chunk per level, from the stage's first level in global memory (signed: the
+    // fused (u, v) launch may have a negative field stride; range checked by tiled_eligible) / from the stage's slot in shared
+    // memory ; OG_NONE = nothing to copy.  Slot 1 (boxes of more than 256 chunks: a few threads of warp 0) is evaluated on the fly.
+    constexpr int OG_NONE = INT_MIN;
+    int og[LPS];
+    uint32_t osm[LPS];
+    {
+        const int crow = threadIdx.x / nck, ck4 = 4 * (threadIdx.x - crow * nck);
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int t = threadIdx.x + k * NTHR_WIN;
-            const int crow = t / nck, ck4 = 4 * (t - crow * nck);
-            crowoff[k] = (td.r0 + crow) * g.ni + td.c0 - 3;
-            cbase[k] = (uint32_t)(crow * pitch - 3) * 4u;
-#pragma unroll
-            for (int l = 0; l < LPS; l++) {
-                const int bm = (int)((dpk >> (2 * l)) & 3u) + crow * pitch;
-                const int j = ((bm & ~3) + ck4) - bm;
-                cj[k] |= (j + 3) << (8 * l);
-                if (crow < nrow && j < td.w) cvalid |= 1u << (4 * k + l);
-            }
+        for (int l = 0; l < LPS; l++) {
+            const int dl = (int)((dpk >> (2 * l)) & 3u);
+            const int phi = (dl + crow * pitch) & 3;
+            const bool ok = crow < nrow && ck4 - phi < td.w;
+            og[l] = ok ? (int)(((long)l * is + (long)(td.r0 + crow) * g.ni + td.c0 + ck4 - phi) * 4) : OG_NONE;
+            osm[l] = (uint32_t)l * capB + (uint32_t)(dl + crow * pitch + ck4 - phi) * 4u;
         }
     }
-    auto sloff = [&](int l) { return (uint32_t)l * capB + ((dpk >> (2 * l)) & 3u) * 4u; };
-    auto issue = [&](int st) {
-        if (cvalid && st < nstages) {
-            const uint32_t sb = smem32 + (uint32_t)(st % NSTAGE) * (LPS * capB);
+    const bool slot1 = (int)threadIdx.x + NTHR_WIN < nrow * nck;
+    auto issue = [&](int st, uint32_t slot) {
+        if (st < nstages) {
+            const uint32_t sb = smem32 + slot * (LPS * capB);
+            const char *pst = reinterpret_cast<const char *>(zin + (long)(st * LPS) * is);
+            const int nl = nf - st * LPS;
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                if ((cvalid >> (4 * k)) & 0xfu) {
-                    const float *p = zin + (long)(st * LPS) * is + crowoff[k];
-#pragma unroll
-                    for (int l = 0; l < LPS; l++) {
-                        if (((cvalid >> (4 * k + l)) & 1u) && st * LPS + l < nf) {
-                            const uint32_t jb = (uint32_t)(cj[k] >> (8 * l)) & 0xffu;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + cbase[k] + sloff(l) + 4u * jb), "l"(p + jb) : "memory");
-                        }
-                        p += is;
+            for (int l = 0; l < LPS; l++)
+                if (og[l] != OG_NONE && l < nl)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + osm[l]), "l"(pst + og[l]) : "memory");
+            if (slot1) {
+                const int tt = threadIdx.x + NTHR_WIN;
+                const int crow = tt / nck, ck4 = 4 * (tt - crow * nck);
+#pragma unroll 1
+                for (int l = 0; l < min(nl, LPS); l++) {
+                    const int dl = (int)((dpk >> (2 * l)) & 3u);
+                    const int phi = (dl + crow * pitch) & 3;
+                    if (ck4 - phi < td.w) {
+                        const float *src = zin + (long)(st * LPS + l) * is + (long)(td.r0 + crow) * g.ni + td.c0 + ck4 - phi;
+                        const uint32_t dst = sb + (uint32_t)l * capB + (uint32_t)(dl + crow * pitch + ck4 - phi) * 4u;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                     }
                 }
             }
@@ -556,85 +466,87 @@ __device__ __forceinline__ void window_all(const GridDev &g, const InterpArgs &a
         __pipeline_commit();
     };
 #pragma unroll 1
-    for (int k = 0; k < NSTAGE; k++) issue(k);
+    for (int k = 0; k < NSTAGE; k++) issue(k, (uint32_t)k);
+
+    // ---- compute side: the plans are loaded / evaluated while the first stages are in flight ----
+    WinThread<DEG> t;
+    bool valid[4] = {false, false, false, false};
+    uint32_t boff = 0;   // byte offset of window element (0, 0) from box element (0, 0)
+#pragma unroll
+    for (int r = 0; r < W; r++) t.roff[r] = (uint32_t)(r * pitch) * 4u;
+    if (fast) {
+        int c0[4], r0[4], wc0 = INT_MAX, wr0 = INT_MAX;
+        float tx[4][4], ty[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            valid[p] = q.valid(p, ni, nj);
+            c0[p] = INT_MAX; r0[p] = INT_MAX; t.sm1[p] = 0.f;
+            if (valid[p]) {
+                const int n = q.index(p, ni);
+                cached_plan<DEG>(g, a, n, c0[p], r0[p], tx[p], ty[p], t.sm1[p]);
+                wc0 = min(wc0, c0[p]); wr0 = min(wr0, r0[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const bool sx = valid[p] && (c0[p] != wc0), sy = valid[p] && (r0[p] != wr0);   // offset 0 or 1 inside the window
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const float lo = (k < S) ? tx[p][k] : 0.f, hi = (k > 0) ? tx[p][k - 1] : 0.f;
+                t.wx[p][k] = valid[p] ? (sx ? hi : lo) : 0.f;
+                const float lo2 = (k < S) ? ty[p][k] : 0.f, hi2 = (k > 0) ? ty[p][k - 1] : 0.f;
+                t.wy[p][k] = valid[p] ? (sy ? hi2 : lo2) : 0.f;
+            }
+        }
+        boff = (uint32_t)((wr0 - td.r0) * pitch + (wc0 - td.c0)) * 4u;
+    }
+    // float2 stores need all four points and 8-byte alignment (even target row length; q.ox is even)
+    const bool full = fast && ((ni & 1) == 0) && valid[3] && ((reinterpret_cast<uintptr_t>(a.zout) & 7) == 0) && ((os & 1) == 0);
+    float *w0 = a.zout + (long)q.oy * ni + q.ox;
     __pipeline_wait_prior(NSTAGE - 1);
     __syncthreads();
 
-    int slot = 0;
+    uint32_t slot = 0;
 #pragma unroll 1
     for (int st = 0; st < nstages; st++) {
-        const float *sbase = smem + slot * LPS * cap + base;
-        const int nl = min(LPS, nf - st * LPS);
+        const uint32_t sb = smem32 + slot * (LPS * capB) + boff;
+        const int nl = nf - st * LPS;
         if (fast) {
-#pragma unroll TILED_UNROLL
-            for (int l = 0; l < nl; l++) {
-                const float *s = sbase + l * cap + ((dpk >> (2 * l)) & 3u);
-                const float zc = s[(W / 2) * pitch + W / 2];
-                const float2 zc2 = make_float2(zc, zc);
-                float2 acc[2];
-#pragma unroll
-                for (int r = 0; r < W; r++) {
-                    float2 d[W];
-#pragma unroll
-                    for (int c = 0; c < W; c++) {
-                        const float v = s[r * pitch + c] - zc;
-                        d[c] = make_float2(v, v);
-                    }
-#pragma unroll
-                    for (int pp = 0; pp < 2; pp++) {
-                        float2 rs = __fmul2_rn(wxp[pp][0], d[0]);
-#pragma unroll
-                        for (int c = 1; c < W; c++) rs = __ffma2_rn(wxp[pp][c], d[c], rs);
-                        acc[pp] = (r == 0) ? __fmul2_rn(wyp[pp][0], rs) : __ffma2_rn(wyp[pp][r], rs, acc[pp]);
-                    }
-                }
-                const float2 r01 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[0], acc[0]));
-                const float2 r23 = __fadd2_rn(zc2, __ffma2_rn(zc2, smp[1], acc[1]));
-                float *w1 = w0 + ni;
-                if (full) {
-                    *reinterpret_cast<float2 *>(w0) = r01;
-                    *reinterpret_cast<float2 *>(w1) = r23;
-                } else {
-                    if (valid[0]) w0[0] = r01.x;
-                    if (valid[1]) w0[1] = r01.y;
-                    if (valid[2]) w1[0] = r23.x;
-                    if (valid[3]) w1[1] = r23.y;
-                }
-                w0 += os;
+            const uint32_t a0 = sb + ((dpk >> 0) & 3u) * 4u, a1 = sb + capB + ((dpk >> 2) & 3u) * 4u;
+            const uint32_t a2 = sb + 2u * capB + ((dpk >> 4) & 3u) * 4u, a3 = sb + 3u * capB + ((dpk >> 6) & 3u) * 4u;
+            if (nl >= LPS) {
+                window_pair<DEG, true>(t, a0, a1, w0, ni, os, full, valid);
+                window_pair<DEG, true>(t, a2, a3, w0 + 2 * os, ni, os, full, valid);
+            } else {   // last stage: 1 .. 3 levels (an absent second level of a pair re-reads the first and is not stored)
+                if (nl >= 2) window_pair<DEG, true>(t, a0, a1, w0, ni, os, full, valid);
+                else window_pair<DEG, false>(t, a0, a0, w0, ni, os, full, valid);
+                if (nl == 3) window_pair<DEG, false>(t, a2, a2, w0 + 2 * os, ni, os, full, valid);
             }
+            w0 += LPS * os;
         }
         __pipeline_wait_prior(NSTAGE - 2);   // stage st + 1 has landed (this thread's share)
         __syncthreads();                     // ... everybody's, and everybody is done reading stage st
-        issue(st + NSTAGE);                  // refill the slot just read
+        issue(st + NSTAGE, slot);            // refill the slot just read
         if (++slot == NSTAGE) slot = 0;
     }
 }
 
+// One CTA per window tile of the compacted list a.win_tiles (k_tile_classify + host compaction: the tiles of the row-separable
+// kernel and the empty ones never launch).  A persistent variant whose copy pipeline ran across tile boundaries (descriptor and
+// plans of the CTA's next tile prefetched) was measured and lost 5-10 %: the hardware's dynamic CTA scheduling de-phases the
+// two resident CTAs of an SM better than a static tile walk does (profiles/r2_window_kernel_log.md).
 template <int DEG>
 __global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) {
     extern __shared__ __align__(16) float smem[];
-    const int by = remap_tile_row(blockIdx.y, gridDim.y);
-    const int tile = by * gridDim.x + blockIdx.x;
+    const int tile = a.win_tiles[blockIdx.x];
     const TileDesc td = a.tiles[tile];
-    if (td.nfast == 0 || td.kind != 0) return;   // kind 1: the row-separable kernel owns the tile
-    for (int k = threadIdx.x; k < NSTAGE * LPS * a.tile_cap; k += NTHR_WIN) smem[k] = 0.f;
-    __syncthreads();
-    if (TILED_NOPROD) {
-        const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
-        const Quad q = quad_of_thread(blockIdx.x, by);
-        if (td.panel) window_all<DEG>(a.src2, a, td, q, fast, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem);
-        else window_all<DEG>(a.src, a, td, q, fast, a.zin, a.src.j2 - a.src.j1 + 1, smem);
-        return;
-    }
-    if (threadIdx.x >= TT * TT) {
-        if (td.panel) producer_warp(a, a.zin + a.panel_stride, td, a.src2.ni, a.src2.j2 - a.src2.j1 + 1, smem, td.w | 1, a.tile_cap);
-        else producer_warp(a, a.zin, td, a.src.ni, a.src.j2 - a.src.j1 + 1, smem, td.w | 1, a.tile_cap);
-        return;
-    }
+    // no zero fill: every cell a fast thread reads lies inside the field (k_tile_classify) and is written by the copies
+    const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(smem);
     const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
-    const Quad q = quad_of_thread(blockIdx.x, by);
-    if (td.panel) compute_warps<DEG>(a.src2, a, td, q, fast, smem);
-    else compute_warps<DEG>(a.src, a, td, q, fast, smem);
+    const int ntx = (a.out_ni + TO - 1) / TO;
+    const Quad q = quad_of_thread(tile % ntx, tile / ntx);
+    if (td.panel) window_tile<DEG>(a.src2, a, td, q, fast, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32);
+    else window_tile<DEG>(a.src, a, td, q, fast, a.zin, a.src.j2 - a.src.j1 + 1, smem32);
 }
 
 }  // namespace

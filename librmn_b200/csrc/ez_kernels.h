@@ -33,6 +33,7 @@ struct InterpArgs {
     int tile_vw;                  // widest row-separable box (<= 32: pitch-33 kernel, else pitch-65 kernel)
     int tile_cap_rs;              // floats per staged source level in the row-separable kernel (pitch x tallest box)
     int ntiles_rowsep, ntiles_window;
+    const int *win_tiles;         // compacted list of the tiles the (persistent) window kernel owns, ntiles_window entries
     int rowsep_enable;            // classification only: allow tiles to be marked row-separable
     // plan cache of the tile plan (per target point: stencil origin, fp32 x / y weights, s = sum wx sum wy - 1), or nullptr:
     // the tile kernels then load 40 B per point instead of redoing the fp64 plan arithmetic in every launch

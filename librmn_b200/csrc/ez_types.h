@@ -58,6 +58,7 @@ struct FieldScalars {
 // field its fast threads read (first column/row, width, height), the Yin-Yang panel it reads from, and counts.
 struct TileDesc {
     int c0, r0, w, h;
-    int panel, nfast, nslow;
+    int panel, nfast;
+    int pitch;  // window kernel: staged row pitch in floats (chosen per tile against bank conflicts)
     int kind;   // 0: 2x2 window kernel (ez_interp_tiled.cuh) ; 1: row-separable kernel (ez_interp_rowsep.cuh)
 };
