@@ -1172,8 +1172,6 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
     return 0;
 }
 
-bool g_warned_polarwind = false;
-
 // uv on device pointers for one plain target (a sub-grid when the caller's target is 'U')
 int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, const float *d_vi, int nfields, long in_stride, long out_stride, int mode) {
     const bool yyin = in.nsubgrids > 0;
@@ -1207,13 +1205,7 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
             Gset *gs = ensure_gset(out, *eff_in);
             if (!gs) return -1;
             if ((gs->counts[1] + gs->counts[2] + gs->counts[3] + gs->counts[4]) > 0) {
-                if (eff_in->needs_expansion || eff_in->axe_y_inverse) {
-                    if (!g_warned_polarwind) {
-                        g_warned_polarwind = true;
-                        fprintf(stderr, "<ezb200> warning: polar wind correction is not applied to hemispheric / y-inverted sources; "
-                                        "vector values in the two source rows next to a pole are plain interpolants\n");
-                    }
-                } else {
+                {
                     const size_t nrow = (size_t)nfields * 2 * eff_in->ni;
                     float *pu = (float *)S.prow[0].get(nrow * sizeof(float)), *pv = (float *)S.prow[1].get(nrow * sizeof(float));
                     if (!pu || !pv) return -1;

@@ -169,10 +169,25 @@ __global__ void __launch_bounds__(256) k_polar_wind(PolarWindArgs a) {
     __shared__ float s_acc[2], s_pole[2];
     const int f = blockIdx.x >> 1, south = blockIdx.x & 1;
     const GridDev &g = a.src;
-    const int ni = g.ni, nj = g.j2 - g.j1 + 1;
-    const int row = south ? 1 : nj;
-    const float *u = a.u + (long)f * a.stride + (long)(row - 1) * ni;
-    const float *v = a.v + (long)f * a.stride + (long)(row - 1) * ni;
+    const int ni = g.ni;
+    // The row next to the pole of the LOGICAL source field (j2 north, j1 south), through the same index folding as the gather
+    // kernels' FieldFetch: hemispheric sources are mirrored about the equator (u symmetric, v antisymmetric, ezuvint.c:65-71),
+    // y-inverted sources are stored north to south.  (The reference hands its pole-wind routines the caller's raw, unexpanded
+    // array together with the expanded row count, ez_corrvec_aunord.c:45-62 -> ez_calcnpolarwind.c:85: it reads past the end of a
+    // hemispheric field and the wrong rows of a y-inverted one; this is the evaluation its own expanded field would give.)
+    int jj = south ? g.j1 : g.j2;
+    float sgn_v = 1.0f;
+    switch (g.xpn) {
+        case XPN_AG_NORTH: if (jj < 1) { jj = 1 - jj; sgn_v = -1.0f; } break;
+        case XPN_AG_SOUTH: if (jj > g.nj) { jj = 2 * g.nj - jj + 1; sgn_v = -1.0f; } break;
+        case XPN_B_NORTH:  if (jj < 1) { jj = 2 - jj; sgn_v = -1.0f; } break;
+        case XPN_B_SOUTH:  if (jj > g.nj) { jj = 2 * g.nj - jj; sgn_v = -1.0f; } break;
+        default: break;
+    }
+    if (g.yinv) jj = g.nj + 1 - jj;
+    const int row = 1;   // (only the longitude of the column enters below)
+    const float *u = a.u + (long)f * a.stride + (long)(jj - 1) * ni;
+    const float *v = a.v + (long)f * a.stride + (long)(jj - 1) * ni;
     const char t = south ? 'S' : 'N';
     const float dgrw = south ? a.dgrw_s : a.dgrw_n;
     const bool weighted = (g.grtyp == 'Z' && g.grref == 'E');
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(256) k_polar_wind(PolarWindArgs a) {
             const int i = i0 + k;
             float plon, plat;
             src_point_lonlat(g, i, row, plon, plat);
-            float z1 = u[i], z2 = v[i];
+            float z1 = u[i], z2 = sgn_v * v[i];
             llwfgdw1('A', 0.f, plon, z1, z2);       // c_gdwdfuv on the auxiliary 'A' grid
             gdwfllw1(t, dgrw, plon, z1, z2);        // c_gduvfwd on the auxiliary polar-stereographic grid
             if (weighted) {
