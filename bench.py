@@ -179,6 +179,15 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     import torch
     import torch.distributed as dist
 
+    t_phase = [time.perf_counter()]
+
+    def phase(what):   # progress on stderr (the JSON line is the only thing on stdout)
+        now = time.perf_counter()
+        if rank == 0:
+            sys.stderr.write("[bench %s arith=%d] %-28s %7.2f s\n" % (name, arith, what, now - t_phase[0]))
+            sys.stderr.flush()
+        t_phase[0] = now
+
     B.set_arith(arith)
     case, nlev, desc = workload(B, name)
     if levels:
@@ -206,6 +215,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     d_out = [torch.empty((nlev, nout), dtype=torch.float32, device="cuda") for _ in range(comps)]
     h_out = [torch.empty((nlev, nout), dtype=torch.float32, pin_memory=True) for _ in range(comps)]
     torch.cuda.synchronize()
+    phase("fields generated + resident")
 
     def step_dev():
         if case.vector:
@@ -227,6 +237,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     for _ in range(max(3, warmup)):
         step_dev()
     torch.cuda.synchronize()
+    phase("gridset build + warm-up")
     if sampler_cb:
         sampler_cb()   # starts the clock sampler: it runs over the timed, the sustained and the e2e regions
 
@@ -260,6 +271,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     ms_per_step = float(t.item()) / steps
     value = world * nout * nlev / (ms_per_step * 1e-3)
 
+    phase("timed steps")
     # ---- sustained: the same step back to back for >= sustain_s seconds (the K-step region above is a burst of tens of ms) ----
     sustained = None
     if sustain_s > 0:
@@ -279,6 +291,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         sustained = {"steps": n_s, "seconds": float(ts.item()) * 1e-3, "ms_per_step": s_ms, "value": world * nout * nlev / (s_ms * 1e-3), "unit": "points/s",
                      "l2": "warm" if flush_buf is not None else "evicted by the step itself"}
 
+    phase("sustained loop")
     # per-kernel durations of the same step, measured live with CUDA events recorded by the library on the launching
     # stream around each kernel (c_ezb200_set_timing): a few extra steps outside the K timed ones
     B.set_timing(True)
@@ -310,8 +323,10 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return float(te.item()) / nsteps
 
+    phase("per-kernel timing")
     e2e_steps = max(3, min(steps, 10))
     e2e_ms = time_host(h_in, h_out, e2e_steps)
+    phase("e2e pinned")
     e2e = {"value": world * nout * nlev / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": comps * nlev * nin * 4,
            "d2h_bytes_per_step": comps * nlev * nout * 4, "ms_per_step": e2e_ms, "host_memory": "pinned"}
     if pageable:
@@ -323,6 +338,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         same = all(np.array_equal(p_out[c], h_out[c].numpy()) for c in range(comps))
         e2e["pageable"]["equals_pinned_result"] = bool(same)
         del p_in, p_out
+        phase("e2e pageable")
 
     # ---- optional collective: gather every rank's level block on every rank (NCCL all-gather over NVLink) ----
     collective = None
@@ -363,6 +379,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         except Exception as ex:
             par = {"checked": "failed: %r" % (ex,), "ok": False}
 
+    phase("collective + parity")
     # ---- roofline of the dominant kernel ----
     peak, peak_kind = measured_peak()
     abytes = algorithmic_bytes(case, nlev)

@@ -14,9 +14,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/ezscint_b200.h"
@@ -97,7 +102,33 @@ struct Grid {   // _Grille, ez_def.h:196-222
     std::map<int, std::unique_ptr<Gset>> gsets; // keyed by gdin (this grid is the target)
 };
 
+// One mutex guards the registry, the gridsets and everything built into them (tile plans, plan caches, rotations).  The
+// reference leaves its tables unguarded and asks callers to define grids serially and then call c_ezdefset / c_ezsint from many
+// threads with their own __thread session (ez_statics.c:12-17).  Here an entry point holds the mutex while it
+// looks grids up, builds what is missing and ENQUEUES its kernels on the calling thread's stream; it lets go of it for
+// everything that blocks on the device or on the host link -- host<->device copies of caller arrays and the final stream
+// synchronisation -- so that the per-thread streams of concurrent callers overlap (Unlocked below).
 std::recursive_mutex g_mtx;
+thread_local int t_lock_depth = 0;
+struct Lock {
+    Lock() { g_mtx.lock(); t_lock_depth++; }
+    ~Lock() { t_lock_depth--; g_mtx.unlock(); }
+    Lock(const Lock &) = delete;
+    Lock &operator=(const Lock &) = delete;
+};
+struct Unlocked {   // releases every level this thread holds for the duration of a blocking call, then takes them back
+    int depth;
+    Unlocked() : depth(t_lock_depth) {
+        for (int k = 0; k < depth; k++) g_mtx.unlock();
+        t_lock_depth = 0;
+    }
+    ~Unlocked() {
+        for (int k = 0; k < depth; k++) g_mtx.lock();
+        t_lock_depth = depth;
+    }
+    Unlocked(const Unlocked &) = delete;
+    Unlocked &operator=(const Unlocked &) = delete;
+};
 std::vector<std::unique_ptr<Grid>> g_grids;
 
 struct DevBuf {
@@ -121,7 +152,9 @@ struct DevBuf {
 struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus per-thread CUDA state
     int gdin = -1, gdout = -1;
     Options opt;
-    cudaStream_t stream = 0;
+    cudaStream_t stream = 0;    // the stream every launch of this thread goes to (c_ezb200_set_stream; default: the legacy default stream)
+    bool stream_user = false;   // set by the caller: never replaced
+    cudaStream_t own_stream = nullptr;   // a private non-blocking stream for host-pointer calls of threads that never set one (HostCallStream)
     int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
     bool timing = false;        // c_ezb200_set_timing: record events around the tile kernels of each interpolation launch
@@ -136,7 +169,6 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     // host-pointer pipeline (ezsint_pipelined): two copy streams beside the compute stream, double-buffered chunks
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    DevBuf pipe_in[2], pipe_out[2];
     DevBuf st_pts[10];          // staging of caller arrays in the scattered-point API
     DevBuf prow[2];             // synthetic pole rows of (u, v) for the polar vector correction (K18)
 };
@@ -412,7 +444,7 @@ int add_grid(std::unique_ptr<Grid> g) {
 }
 
 int gdef_fmem(int ni, int nj, const char *grtyp, const char *grref, int ig1, int ig2, int ig3, int ig4, const float *ax, const float *ay) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     const char t = grtyp[0];
     const int ig[4] = {ig1, ig2, ig3, ig4};
     if (ni <= 0 || nj <= 0) {
@@ -833,6 +865,7 @@ int stage_in(Staged &s, DevBuf &buf, const float *p, size_t n) {
     if (is_device_ptr(p)) { s.dev = const_cast<float *>(p); return 0; }
     s.dev = (float *)buf.get(n * sizeof(float));
     if (!s.dev) { fprintf(stderr, "<ezb200> cannot allocate %zu bytes of device staging\n", n * sizeof(float)); return -1; }
+    Unlocked u;   // a copy from pageable memory blocks the calling thread until it has been staged
     CUDA_OK(cudaMemcpyAsync(s.dev, p, n * sizeof(float), cudaMemcpyHostToDevice, S.stream));
     return 0;
 }
@@ -846,6 +879,7 @@ int stage_out(Staged &s, DevBuf &buf, float *p, size_t n) {
 }
 int finish_out(Staged &s) {
     if (!s.host) return 0;
+    Unlocked u;
     CUDA_OK(cudaMemcpyAsync(s.host, s.dev, s.n * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
     CUDA_OK(cudaStreamSynchronize(S.stream));
     return 0;
@@ -1047,6 +1081,26 @@ int sint_any_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfi
     return 0;
 }
 
+// A call whose arrays all live in host memory is synchronous by construction (the results are back in the caller's arrays when
+// it returns), so it does not have to be ordered with anything the caller queued on the legacy default stream: threads that
+// never chose a stream run such calls on a private non-blocking stream, and concurrent host threads overlap on the device
+// instead of serialising on stream 0.  Device-pointer calls keep the caller's (or the default) stream semantics.
+struct HostCallStream {
+    cudaStream_t saved;
+    bool active = false;
+    explicit HostCallStream(bool all_host) : saved(S.stream) {
+        if (!all_host || S.stream_user) return;
+        if (!S.own_stream && cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            (void)cudaGetLastError();
+            S.own_stream = nullptr;
+            return;
+        }
+        S.stream = S.own_stream;
+        active = true;
+    }
+    ~HostCallStream() { if (active) S.stream = saved; }
+};
+
 bool session_ok(const char *who) {
     if (S.gdin == -1 || S.gdout == -1 || !grid_of(S.gdin) || !grid_of(S.gdout)) {
         fprintf(stderr, "<%s> Source or target grid undefined! Aborting...\n", who);
@@ -1067,54 +1121,216 @@ int ensure_pipe() {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// host-pointer calls: the level-chunk pipeline
+// ---------------------------------------------------------------------------------------------------
+// Host-side copy pool for PAGEABLE caller arrays.  cudaMemcpyAsync from / to plain malloc'ed memory is staged by the driver
+// through one bounce buffer and blocks the calling thread (measured: 16 GB/s, 4x below the pinned rate, and it serialises the
+// three-stream pipeline).  Here pageable chunks go through a pinned ring owned by the session: a few helper threads (plus the
+// caller) memcpy the chunk into / out of the ring while the DMA engines and the kernels work on the neighbouring chunks.
+class CopyPool {
+    struct Batch {   // lives on the waiter's stack: `left` only changes under `m`, so the waiter cannot leave while a worker still holds it
+        int left = 0;
+        std::mutex m;
+        std::condition_variable cv;
+    };
+    struct Job { char *dst; const char *src; size_t n; Batch *b; };
+    std::vector<std::thread> threads;
+    std::deque<Job> q;
+    std::mutex m;
+    std::condition_variable cv;
+    bool started = false;
+    int nthreads = 0;
+
+    void worker() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return !q.empty(); });
+                j = q.front();
+                q.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+            {
+                std::lock_guard<std::mutex> lk(j.b->m);
+                if (--j.b->left == 0) j.b->cv.notify_all();
+            }
+        }
+    }
+
+public:
+    int helpers() {
+        std::lock_guard<std::mutex> lk(m);
+        if (!started) {
+            started = true;
+            const char *e = getenv("EZB200_COPY_THREADS");
+            unsigned hw = std::thread::hardware_concurrency();
+            nthreads = e ? atoi(e) : (int)(hw >= 16 ? 7 : (hw >= 8 ? 3 : 1));
+            if (nthreads < 0) nthreads = 0;
+            if (nthreads > 31) nthreads = 31;
+            for (int k = 0; k < nthreads; k++) {
+                threads.emplace_back([this] { worker(); });
+                threads.back().detach();   // the pool lives as long as the process
+            }
+        }
+        return nthreads;
+    }
+    // blocking parallel memcpy: the caller copies one slice itself
+    void copy(void *dst, const void *src, size_t bytes) {
+        const int nh = helpers();
+        const size_t slice_min = (size_t)1 << 20;
+        int parts = (int)std::min<size_t>((size_t)nh + 1, (bytes + slice_min - 1) / slice_min);
+        if (parts <= 1) { memcpy(dst, src, bytes); return; }
+        Batch b;
+        const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+        int njobs = 0;
+        for (int k = 1; k < parts; k++)
+            if (per * k < bytes) njobs++;
+        b.left = njobs;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (int k = 1; k < parts; k++) {
+                const size_t o = per * k;
+                if (o >= bytes) continue;
+                q.push_back(Job{(char *)dst + o, (const char *)src + o, std::min(per, bytes - o), &b});
+            }
+        }
+        cv.notify_all();
+        memcpy(dst, src, std::min(per, bytes));
+        std::unique_lock<std::mutex> lk(b.m);
+        b.cv.wait(lk, [&] { return b.left <= 0; });
+    }
+};
+// never destroyed: its helper threads wait on its condition variable until the process ends (destroying a condition variable
+// with waiters blocks in pthread_cond_destroy)
+CopyPool &g_copy_pool = *new CopyPool;
+
+struct PinBuf {   // pinned host ring slot
+    void *p = nullptr;
+    size_t cap = 0;
+    void *get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return nullptr; }
+            cap = bytes;
+        }
+        return p;
+    }
+};
+thread_local PinBuf t_pin_in[2][2], t_pin_out[2][2];
+thread_local DevBuf t_pipe_in[2][2], t_pipe_out[2][2];
+
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 // Host arrays in, host arrays out, several fields: the fields are cut into chunks of levels and the three legs
 // (host->device copy, interpolation, device->host copy) run on three streams, so that the PCIe link carries
-// inputs of chunk k+1 and outputs of chunk k-1 (full duplex) while chunk k is being interpolated.
-int ezsint_pipelined(Grid &out, Grid &in, float *zout, const float *zin, int nfields, size_t nin, size_t nout) {
+// inputs of chunk k+1 and outputs of chunk k-1 (full duplex) while chunk k is being interpolated.  One or two input
+// arrays and one or two output arrays (c_ezsint / c_ezuvint).  compute(d_in0, d_in1, d_out0, d_out1, nf) enqueues the
+// interpolation of nf fields on S.stream and returns the reference's return code.
+struct PipeSpec {
+    int narr;                    // 1 (scalar) or 2 (u, v)
+    const float *in[2];
+    float *out[2];
+    size_t nin, nout;            // floats per field
+    int nfields;
+};
+template <class F>
+int host_pipeline(const PipeSpec &p, F compute) {
     if (ensure_pipe() < 0) return -1;
+    const int nfields = p.nfields;
     const int chunk = nfields >= 16 ? 4 : (nfields >= 4 ? 2 : 1);
-    float *d_in[2], *d_out[2];
-    for (int k = 0; k < 2; k++) {
-        d_in[k] = (float *)S.pipe_in[k].get(nin * chunk * sizeof(float));
-        d_out[k] = (float *)S.pipe_out[k].get(nout * chunk * sizeof(float));
-        if (!d_in[k] || !d_out[k]) { fprintf(stderr, "<ezb200> cannot allocate device staging for the host-pointer pipeline\n"); return -1; }
-    }
+    bool in_pg = false, out_pg = false;
+    for (int a = 0; a < p.narr; a++) { in_pg |= !is_pinned_host(p.in[a]); out_pg |= !is_pinned_host(p.out[a]); }
+    static const bool ring_on = !(getenv("EZB200_PINNED_RING") && atoi(getenv("EZB200_PINNED_RING")) == 0);
+    if (!ring_on) in_pg = out_pg = false;
+    float *d_in[2][2], *d_out[2][2], *h_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *h_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    for (int a = 0; a < p.narr; a++)
+        for (int k = 0; k < 2; k++) {
+            d_in[a][k] = (float *)t_pipe_in[a][k].get(p.nin * chunk * sizeof(float));
+            d_out[a][k] = (float *)t_pipe_out[a][k].get(p.nout * chunk * sizeof(float));
+            if (!d_in[a][k] || !d_out[a][k]) { fprintf(stderr, "<ezb200> cannot allocate device staging for the host-pointer pipeline\n"); return -1; }
+            if (in_pg) h_in[a][k] = (float *)t_pin_in[a][k].get(p.nin * chunk * sizeof(float));
+            if (out_pg) h_out[a][k] = (float *)t_pin_out[a][k].get(p.nout * chunk * sizeof(float));
+            if ((in_pg && !h_in[a][k]) || (out_pg && !h_out[a][k])) { in_pg = out_pg = false; }   // no pinned memory: plain copies
+        }
     // the copy streams must not run ahead of work already queued on the caller's stream
     CUDA_OK(cudaEventRecord(S.ev_comp[0], S.stream));
     CUDA_OK(cudaStreamWaitEvent(S.s_h2d, S.ev_comp[0], 0));
     int rc = 0, c = 0;
+    int prev_f0 = 0, prev_nf = 0;
+    auto fail = [&](int r) { Unlocked u; cudaStreamSynchronize(S.s_h2d); cudaStreamSynchronize(S.stream); cudaStreamSynchronize(S.s_d2h); return r; };
+    auto drain = [&](int b, int f0, int nf) -> int {   // pageable outputs: ring slot b -> the caller's arrays
+        Unlocked u;
+        CUDA_OK(cudaEventSynchronize(S.ev_out[b]));
+        for (int a = 0; a < p.narr; a++) g_copy_pool.copy(p.out[a] + (size_t)f0 * p.nout, h_out[a][b], p.nout * nf * sizeof(float));
+        return 0;
+    };
     for (int f0 = 0; f0 < nfields; f0 += chunk, c++) {
         const int nf = (nfields - f0 < chunk) ? (nfields - f0) : chunk, b = c & 1;
-        if (c >= 2) CUDA_OK(cudaStreamWaitEvent(S.s_h2d, S.ev_comp[b], 0));      // the kernel that read this input buffer is done
-        CUDA_OK(cudaMemcpyAsync(d_in[b], zin + (size_t)f0 * nin, nin * nf * sizeof(float), cudaMemcpyHostToDevice, S.s_h2d));
+        {
+            Unlocked u;   // nothing below touches the registry; copies from pageable memory block
+            if (in_pg) {
+                if (c >= 2) CUDA_OK(cudaEventSynchronize(S.ev_in[b]));     // the DMA that read this ring slot is done
+                for (int a = 0; a < p.narr; a++) g_copy_pool.copy(h_in[a][b], p.in[a] + (size_t)f0 * p.nin, p.nin * nf * sizeof(float));
+            }
+            if (c >= 2) CUDA_OK(cudaStreamWaitEvent(S.s_h2d, S.ev_comp[b], 0));      // the kernel that read this input buffer is done
+            for (int a = 0; a < p.narr; a++)
+                CUDA_OK(cudaMemcpyAsync(d_in[a][b], in_pg ? h_in[a][b] : p.in[a] + (size_t)f0 * p.nin, p.nin * nf * sizeof(float), cudaMemcpyHostToDevice, S.s_h2d));
+        }
         CUDA_OK(cudaEventRecord(S.ev_in[b], S.s_h2d));
         CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_in[b], 0));
         if (c >= 2) CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_out[b], 0));      // the copy that drained this output buffer is done
-        int r = sint_any_dev(out, in, d_out[b], d_in[b], nf, (long)nin, (long)nout, 0, 1);
-        if (r < 0) { cudaStreamSynchronize(S.s_h2d); cudaStreamSynchronize(S.stream); cudaStreamSynchronize(S.s_d2h); return r; }
+        int r = compute(d_in[0][b], d_in[1][b], d_out[0][b], d_out[1][b], nf);
+        if (r < 0) return fail(r);
         if (r > rc) rc = r;
         CUDA_OK(cudaEventRecord(S.ev_comp[b], S.stream));
         CUDA_OK(cudaStreamWaitEvent(S.s_d2h, S.ev_comp[b], 0));
-        CUDA_OK(cudaMemcpyAsync(zout + (size_t)f0 * nout, d_out[b], nout * nf * sizeof(float), cudaMemcpyDeviceToHost, S.s_d2h));
+        {
+            Unlocked u;
+            for (int a = 0; a < p.narr; a++)
+                CUDA_OK(cudaMemcpyAsync(out_pg ? h_out[a][b] : p.out[a] + (size_t)f0 * p.nout, d_out[a][b], p.nout * nf * sizeof(float), cudaMemcpyDeviceToHost, S.s_d2h));
+        }
         CUDA_OK(cudaEventRecord(S.ev_out[b], S.s_d2h));
+        if (out_pg && c >= 1 && drain(b ^ 1, prev_f0, prev_nf) < 0) return fail(-1);   // the previous chunk leaves the ring while this one is in flight
+        prev_f0 = f0; prev_nf = nf;
     }
+    if (out_pg && c >= 1 && drain((c - 1) & 1, prev_f0, prev_nf) < 0) return fail(-1);
+    Unlocked u;
     CUDA_OK(cudaStreamSynchronize(S.s_d2h));
     CUDA_OK(cudaStreamSynchronize(S.stream));
     return rc;
 }
 
+int ezsint_pipelined(Grid &out, Grid &in, float *zout, const float *zin, int nfields, size_t nin, size_t nout) {
+    PipeSpec p;
+    p.narr = 1; p.in[0] = zin; p.in[1] = nullptr; p.out[0] = zout; p.out[1] = nullptr;
+    p.nin = nin; p.nout = nout; p.nfields = nfields;
+    return host_pipeline(p, [&](float *di, float *, float *dout, float *, int nf) {
+        return sint_any_dev(out, in, dout, di, nf, (long)nin, (long)nout, 0, 1);
+    });
+}
+
 int ezsint_n(float *zout, float *zin, int nfields) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     if (!session_ok("c_ezsint")) return -1;
     if (nfields < 1) return -1;
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
     const size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
     if (S.gdin == S.gdout) {   // ezsint.c:56-60
+        Unlocked u;
         CUDA_OK(cudaMemcpyAsync(zout, zin, nin * nfields * sizeof(float), cudaMemcpyDefault, S.stream));
         CUDA_OK(cudaStreamSynchronize(S.stream));
         return 1;
     }
-    if (nfields >= 2 && !is_device_ptr(zin) && !is_device_ptr(zout)) return ezsint_pipelined(out, in, zout, zin, nfields, nin, nout);
+    const bool all_host = !is_device_ptr(zin) && !is_device_ptr(zout);
+    HostCallStream hs(all_host);
+    if (nfields >= 2 && all_host) return ezsint_pipelined(out, in, zout, zin, nfields, nin, nout);
     Staged si, so;
     if (stage_in(si, S.st_in[0], zin, nin * nfields) < 0) return -1;
     if (stage_out(so, S.st_out[0], zout, nout * nfields) < 0) return -1;
@@ -1230,7 +1446,9 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
                 }
             }
         }
-        if (nfields == 1 && !prow_u && !prow_v && !eff_in->needs_expansion) {
+        const long uv_in = (long)(vi - ui), uv_out = (long)(d_vo - d_uo);
+        const bool uv_near = (uv_in < 0 ? -uv_in : uv_in) < (1L << 26) && (uv_out < 0 ? -uv_out : uv_out) < (1L << 40);
+        if (nfields == 1 && !prow_u && !prow_v && !eff_in->needs_expansion && uv_near) {
             // one (u, v) pair, no synthetic pole rows, no hemispheric mirror (the only place the two components are treated
             // differently): ONE launch over two "fields" whose stride is the distance between the caller's arrays, so the
             // gridset, the plans and the tile setup are read and built once for both components
@@ -1246,28 +1464,40 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
 }
 
 int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields, int mode) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     if (!session_ok("c_ezuvint")) return -1;
     if (nfields < 1 || check_degree() < 0) return -1;
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
     const size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
+    if (out.nsubgrids > 0 && in.nsubgrids > 0 && S.opt.use_1subgrid == 1) {
+        fprintf(stderr, "<c_ezyyuvint> cannot use 1 subgrid to interpolate to a Yin-Yang grid  Aborting...\n");
+        return -1;
+    }
+    // device part: one plain target, or the two sub-grids of a 'U' target (ezyyuvint.c:28-319)
+    auto on_device = [&](float *d_uo, float *d_vo, const float *d_ui, const float *d_vi, int nf) -> int {
+        if (out.nsubgrids > 0) {
+            Grid *yin_out = grid_of(out.subgrid[0]), *yan_out = grid_of(out.subgrid[1]);
+            if (!yin_out || !yan_out) return -1;
+            const long half = (long)yin_out->ni * yin_out->nj;
+            int r1 = uvint_dev(*yin_out, in, d_uo, d_vo, d_ui, d_vi, nf, (long)nin, (long)nout, mode);
+            int r2 = uvint_dev(*yan_out, in, d_uo + half, d_vo + half, d_ui, d_vi, nf, (long)nin, (long)nout, mode);
+            return (r1 < 0 || r2 < 0) ? -1 : ((r1 == 2 || r2 == 2) ? 2 : 0);
+        }
+        return uvint_dev(out, in, d_uo, d_vo, d_ui, d_vi, nf, (long)nin, (long)nout, mode);
+    };
+    const bool all_host = !is_device_ptr(uuin) && !is_device_ptr(vvin) && !is_device_ptr(uuout) && !is_device_ptr(vvout);
+    HostCallStream hs(all_host);
+    if (all_host && nfields >= 2) {   // the level-chunk pipeline of the scalar path, two arrays each way
+        PipeSpec p;
+        p.narr = 2; p.in[0] = uuin; p.in[1] = vvin; p.out[0] = uuout; p.out[1] = vvout;
+        p.nin = nin; p.nout = nout; p.nfields = nfields;
+        return host_pipeline(p, [&](float *du, float *dv, float *duo, float *dvo, int nf) { return on_device(duo, dvo, du, dv, nf); });
+    }
     Staged su, sv, ou, ov;
     if (stage_in(su, S.st_in[0], uuin, nin * nfields) < 0 || stage_in(sv, S.st_in[1], vvin, nin * nfields) < 0) return -1;
     if (stage_out(ou, S.st_out[0], uuout, nout * nfields) < 0 || stage_out(ov, S.st_out[1], vvout, nout * nfields) < 0) return -1;
-    int rc;
-    if (out.nsubgrids > 0) {
-        if (in.nsubgrids > 0 && S.opt.use_1subgrid == 1) {
-            fprintf(stderr, "<c_ezyyuvint> cannot use 1 subgrid to interpolate to a Yin-Yang grid  Aborting...\n");
-            return -1;
-        }
-        Grid *yin_out = grid_of(out.subgrid[0]), *yan_out = grid_of(out.subgrid[1]);
-        const long half = (long)yin_out->ni * yin_out->nj;
-        int r1 = uvint_dev(*yin_out, in, ou.dev, ov.dev, su.dev, sv.dev, nfields, (long)nin, (long)nout, mode);
-        int r2 = uvint_dev(*yan_out, in, ou.dev + half, ov.dev + half, su.dev, sv.dev, nfields, (long)nin, (long)nout, mode);
-        rc = (r1 < 0 || r2 < 0) ? -1 : ((r1 == 2 || r2 == 2) ? 2 : 0);
-    } else {
-        rc = uvint_dev(out, in, ou.dev, ov.dev, su.dev, sv.dev, nfields, (long)nin, (long)nout, mode);
-    }
+    int rc = on_device(ou.dev, ov.dev, su.dev, sv.dev, nfields);
+    if (rc < 0) return rc;
     if (finish_out(ou) < 0 || finish_out(ov) < 0) return -1;
     return rc;
 }
@@ -1304,6 +1534,7 @@ const char *c_ezb200_version(void) { return "ezb200 0.1 (sm_100a)"; }
 
 int32_t c_ezb200_set_stream(void *stream) {
     S.stream = (cudaStream_t)stream;
+    S.stream_user = true;
     return 0;
 }
 int32_t c_ezb200_set_arith(int32_t mode) {
@@ -1404,7 +1635,7 @@ int32_t ezgdef_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1
 }
 
 int32_t c_ezgdef_supergrid(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t vercode, int32_t nsubgrids, int32_t *subgrid) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     if (nsubgrids <= 1) {
         fprintf(stderr, "<c_ezgdef_supergrid> nsubgrids given is less than 2! Aborting...\n");
         return -1;
@@ -1450,7 +1681,7 @@ int32_t ezgdef_supergrid_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, in
 }
 
 int32_t c_gdrls(int32_t gdin) {   // gdrls.c:34-90
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdin);
     if (!g) return 0;
     if (g->access_count > 0) g->access_count--;
@@ -1472,7 +1703,7 @@ int32_t gdrls_(int32_t *gdin) { return c_gdrls(*gdin); }
 
 // ---- queries ----
 int32_t c_ezgprm(int32_t gdid, char *grtyp, int32_t *ni, int32_t *nj, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     *grtyp = g->grtyp; *ni = g->ni; *nj = g->nj;
@@ -1488,7 +1719,7 @@ int32_t ezgprm_(int32_t *gdid, char *grtyp, int32_t *ni, int32_t *nj, int32_t *i
 }
 int32_t c_ezgxprm(int32_t gdid, int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, char *grref,
                   int32_t *ig1ref, int32_t *ig2ref, int32_t *ig3ref, int32_t *ig4ref) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     *ni = g->ni; *nj = g->nj;
@@ -1508,14 +1739,14 @@ int32_t ezgxprm_(int32_t *gdid, int32_t *ni, int32_t *nj, char *grtyp, int32_t *
     return rc;
 }
 int32_t c_ezget_nsubgrids(int32_t gdid) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     return g->nsubgrids == 0 ? 1 : g->nsubgrids;
 }
 int32_t ezget_nsubgrids_(int32_t *gdid) { return c_ezget_nsubgrids(*gdid); }
 int32_t c_ezget_subgridids(int32_t gdid, int32_t *subgrid) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     if (g->nsubgrids == 0) { *subgrid = gdid; return 1; }
@@ -1525,7 +1756,7 @@ int32_t c_ezget_subgridids(int32_t gdid, int32_t *subgrid) {
 int32_t ezget_subgridids_(int32_t *gdid, int32_t *subgrid) { return c_ezget_subgridids(*gdid, subgrid); }
 
 int32_t c_gdll(int32_t gdid, float *lat, float *lon) {   // gdll.c:25-73
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     if (g->nsubgrids > 0) {
@@ -1648,7 +1879,7 @@ int wind_points_dev(Grid &g, float *d_u, float *d_v, const float *d_lat, const f
 }  // namespace
 
 int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int32_t n) {   // gdxyfll.c:190-243
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || n < 0) return -1;
     if (n == 0) return 0;
@@ -1660,7 +1891,7 @@ int32_t c_gdxyfll(int32_t gdid, float *x, float *y, float *lat, float *lon, int3
 int32_t gdxyfll_(int32_t *gdid, float *x, float *y, float *lat, float *lon, int32_t *n) { return c_gdxyfll(*gdid, x, y, lat, lon, *n); }
 
 int32_t c_gdllfxy(int32_t gdid, float *lat, float *lon, float *x, float *y, int32_t n) {   // gdllfxy.c:30-92
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || n < 0) return -1;
     if (g->grtyp == 'Y') {
@@ -1680,7 +1911,7 @@ int32_t c_gdllfxy(int32_t gdid, float *lat, float *lon, float *x, float *y, int3
 int32_t gdllfxy_(int32_t *gdid, float *lat, float *lon, float *x, float *y, int32_t *n) { return c_gdllfxy(*gdid, lat, lon, x, y, *n); }
 
 int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, int32_t n) {   // gdxysval.c:50-116
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdin);
     if (!g || n < 0) return -1;
     if (n == 0) return 0;
@@ -1692,7 +1923,7 @@ int32_t c_gdxysval(int32_t gdin, float *zout, float *zin, float *x, float *y, in
 int32_t gdxysval_(int32_t *gdin, float *zout, float *zin, float *x, float *y, int32_t *n) { return c_gdxysval(*gdin, zout, zin, x, y, *n); }
 
 int32_t c_gdllsval(int32_t gdid, float *zout, float *zin, float *lat, float *lon, int32_t n) {   // gdllsval.c:35-55
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || n < 0) return -1;
     if (n == 0) return 0;
@@ -1707,7 +1938,7 @@ int32_t gdllsval_(int32_t *gdid, float *zout, float *zin, float *lat, float *lon
 
 // c_gdxyvval (gdxyvval.c:38-116): both components at caller-supplied x, y, as GRID components (no rotation)
 int32_t c_gdxyvval(int32_t gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t n) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdin);
     if (!g || n < 0) return -1;
     if (n == 0) return 0;
@@ -1722,7 +1953,7 @@ int32_t gdxyvval_(int32_t *gdin, float *uuout, float *vvout, float *uuin, float 
 }
 
 int32_t c_gdllvval(int32_t gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t n) {   // gdllvval.c:37-58
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || n < 0) return -1;
     if (g->nsubgrids > 0) {
@@ -1745,7 +1976,7 @@ int32_t gdllvval_(int32_t *gdid, float *uuout, float *vvout, float *uuin, float 
 
 // c_gdwdfuv (gdwdfuv.c:100-113) / c_gduvfwd (gduvfwd.c:112-125): wind conversions at caller-supplied lat/lon
 int32_t c_gdwdfuv(int32_t gdid, float *spd_out, float *wd_out, float *uuin, float *vvin, float *latin, float *lonin, int32_t npts) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || npts < 0) return -1;
     if (g->nsubgrids > 0) {
@@ -1766,7 +1997,7 @@ int32_t gdwdfuv_(int32_t *gdid, float *spd_out, float *wd_out, float *uuin, floa
     return c_gdwdfuv(*gdid, spd_out, wd_out, uuin, vvin, latin, lonin, *npts);
 }
 int32_t c_gduvfwd(int32_t gdid, float *uugdout, float *vvgdout, float *uullin, float *vvllin, float *latin, float *lonin, int32_t npts) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || npts < 0) return -1;
     if (g->nsubgrids > 0) {
@@ -1798,7 +2029,7 @@ int wdval_common(Grid &g, float *ou, float *ov, const float *du, const float *dv
 }
 }  // namespace
 int32_t c_gdllwdval(int32_t gdid, float *uuout, float *vvout, float *uuin, float *vvin, float *lat, float *lon, int32_t n) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g || n < 0) return -1;
     if (n == 0) return 0;
@@ -1814,7 +2045,7 @@ int32_t gdllwdval_(int32_t *gdid, float *uuout, float *vvout, float *uuin, float
     return c_gdllwdval(*gdid, uuout, vvout, uuin, vvin, lat, lon, *n);
 }
 int32_t c_gdxywdval(int32_t gdin, float *uuout, float *vvout, float *uuin, float *vvin, float *x, float *y, int32_t n) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdin);
     if (!g || n < 0) return -1;
     if (g->grtyp == 'Y') return -1;
@@ -1837,7 +2068,7 @@ int32_t gdxywdval_(int32_t *gdin, float *uuout, float *vvout, float *uuin, float
 }
 
 int c_gdsetmask(int gdid, int *mask) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     if (g->nsubgrids > 0) { fprintf(stderr, "<gdsetmask> This operation is not supported for 'U' grids.\n"); return -1; }
@@ -1847,7 +2078,7 @@ int c_gdsetmask(int gdid, int *mask) {
 }
 int gdsetmask_(int *gdid, int *mask) { return c_gdsetmask(*gdid, mask); }
 int c_gdgetmask(int gdid, int *mask) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *g = grid_of(gdid);
     if (!g) return -1;
     if (g->nsubgrids > 0) { fprintf(stderr, "<gdgetmask> This operation is not supported for 'U' grids.\n"); return -1; }
@@ -1859,7 +2090,7 @@ int gdgetmask_(int *gdid, int *mask) { return c_gdgetmask(*gdid, mask); }
 
 // ---- gridset selection ----
 int32_t c_ezdefset(int32_t gdout, int32_t gdin) {   // ezdefset.c:38-170 ; the x/y arrays are built lazily by the first compute call
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     if (gdout == -1 && gdin != -1) gdout = gdin;
     if (!grid_of(gdin) || !grid_of(gdout)) {
         fprintf(stderr, "<c_ezdefset> undefined grid id (gdout=%d gdin=%d)\n", gdout, gdin);
@@ -1896,7 +2127,7 @@ int32_t c_ezwdint(float *spdout, float *wdout, float *uuin, float *vvin) { retur
 int32_t ezwdint_(float *spdout, float *wdout, float *uuin, float *vvin) { return c_ezwdint(spdout, wdout, uuin, vvin); }
 
 int c_ezsint_mask(int *mask_out, int *mask_in) {   // ez_mask.c:184-223
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     if (!session_ok("ezsint_mask")) return -1;
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
     if (in.nsubgrids > 0 || out.nsubgrids > 0) {
@@ -1923,7 +2154,7 @@ int c_ezsint_mask(int *mask_out, int *mask_in) {   // ez_mask.c:184-223
 int ezsint_mask_(int *mask_out, int *mask_in) { return c_ezsint_mask(mask_out, mask_in); }
 
 int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, uint8_t *zonebits, int32_t *counts) {
-    std::lock_guard<std::recursive_mutex> lk(g_mtx);
+    Lock lk;
     Grid *o = grid_of(gdout), *i = grid_of(gdin);
     if (!o || !i || o->nsubgrids > 0) return -1;
     Gset *gs = ensure_gset(*o, *i);
