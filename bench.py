@@ -194,6 +194,16 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         nlev = levels
     nin, nout = case.n_src, case.n_out
     case.defset()
+    # fewer fields than GPUs (single-call workloads C1 / C3 / C4 at N > 1): the target ROWS are split over the ranks instead of
+    # the levels; every rank holds the whole source field and produces its band of whole tile rows
+    band_mode = world > 1 and nlev < world and case.dst_shape[0] >= 32 * world
+    nout_full = nout
+    if band_mode:
+        from librmn_b200 import sharding
+        j0, j1 = sharding.row_band(case.dst_shape[0], rank, world)
+        B.set_rows(j0, j1)
+        nout = (j1 - j0) * case.dst_shape[1]
+    work_scale = (1.0 / world) if band_mode else 1.0   # points per step summed over the ranks = world * nout_full * nlev * work_scale
 
     def barrier():
         if world > 1:
@@ -269,7 +279,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / steps
-    value = world * nout * nlev / (ms_per_step * 1e-3)
+    value = world * nout_full * work_scale * nlev / (ms_per_step * 1e-3)
 
     phase("timed steps")
     # ---- sustained: the same step back to back for >= sustain_s seconds (the K-step region above is a burst of tens of ms) ----
@@ -288,7 +298,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         if world > 1:
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         s_ms = float(ts.item()) / n_s
-        sustained = {"steps": n_s, "seconds": float(ts.item()) * 1e-3, "ms_per_step": s_ms, "value": world * nout * nlev / (s_ms * 1e-3), "unit": "points/s",
+        sustained = {"steps": n_s, "seconds": float(ts.item()) * 1e-3, "ms_per_step": s_ms, "value": world * nout_full * work_scale * nlev / (s_ms * 1e-3), "unit": "points/s",
                      "l2": "warm" if flush_buf is not None else "evicted by the step itself"}
 
     phase("sustained loop")
@@ -327,14 +337,14 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     e2e_steps = max(3, min(steps, 10))
     e2e_ms = time_host(h_in, h_out, e2e_steps)
     phase("e2e pinned")
-    e2e = {"value": world * nout * nlev / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": comps * nlev * nin * 4,
+    e2e = {"value": world * nout_full * work_scale * nlev / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": comps * nlev * nin * 4,
            "d2h_bytes_per_step": comps * nlev * nout * 4, "ms_per_step": e2e_ms, "host_memory": "pinned"}
     if pageable:
         # what an unmodified caller hands over: plain (malloc) arrays
         p_in = [np.array(h.numpy(), copy=True) for h in h_in]
         p_out = [np.empty((nlev, nout), np.float32) for _ in range(comps)]
         pg_ms = time_host(p_in, p_out, max(2, e2e_steps // 2))
-        e2e["pageable"] = {"value": world * nout * nlev / (pg_ms * 1e-3), "unit": "points/s", "ms_per_step": pg_ms, "host_memory": "pageable (malloc)"}
+        e2e["pageable"] = {"value": world * nout_full * work_scale * nlev / (pg_ms * 1e-3), "unit": "points/s", "ms_per_step": pg_ms, "host_memory": "pageable (malloc)"}
         same = all(np.array_equal(p_out[c], h_out[c].numpy()) for c in range(comps))
         e2e["pageable"]["equals_pinned_result"] = bool(same)
         del p_in, p_out
@@ -344,21 +354,30 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     collective = None
     if gather and world > 1:
         from librmn_b200 import sharding
+
+        def do_gather():
+            if band_mode:
+                return sharding.gather_rows(d_out[0].view(nlev, -1, case.dst_shape[1])[0], case.dst_shape[0])
+            return sharding.gather_levels(d_out[0], world * nlev)
+
         for _ in range(2):
-            sharding.gather_levels(d_out[0], world)
+            do_gather()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         nrep = 5
         for _ in range(nrep):
-            full = sharding.gather_levels(d_out[0], world)
+            full = do_gather()
         g1.record()
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1) / nrep], dtype=torch.float64, device="cuda")
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gms = float(tg.item())
-        collective = {"op": "all_gather of %d x %d levels of %d points (NCCL)" % (world, nlev, nout), "ms": gms, "ms_per_level": gms / (world * nlev),
-                      "bytes_received_per_rank": (world - 1) * nlev * nout * 4, "GBps_per_rank": (world - 1) * nlev * nout * 4 / (gms * 1e-3) / 1e9,
+        recv = ((nout_full - nout) if band_mode else (world - 1) * nlev * nout) * 4
+        collective = {"op": ("all_gather of %d row bands of one %d-point field (NCCL, padded to the tallest band)" % (world, nout_full)) if band_mode else (
+                          "all_gather of %d x %d levels of %d points (NCCL)" % (world, nlev, nout)),
+                      "ms": gms, "ms_per_level": gms / (1 if band_mode else world * nlev),
+                      "bytes_received_per_rank": recv, "GBps_per_rank": recv / (gms * 1e-3) / 1e9,
                       "kernel_ms_per_step": ms_per_step, "gathered_shape": list(full.shape)}
         del full
 
@@ -370,6 +389,8 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
             torch.cuda.synchronize()
             got = np.stack([d_out[c][0].cpu().numpy() for c in range(comps)])
             rc_r, ref, rng = oracle_level(name)
+            if band_mode:
+                ref = ref.reshape(comps, case.dst_shape[0], case.dst_shape[1])[:, j0:j1].reshape(comps, -1)
             d = np.abs(got.astype(np.float64) - ref) / rng
             # Yin-Yang: the panel choice of a point exactly on the mask border may flip (a handful of points at most)
             nbad = int((d > 1e-5).sum())
@@ -382,7 +403,7 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
     phase("collective + parity")
     # ---- roofline of the dominant kernel ----
     peak, peak_kind = measured_peak()
-    abytes = algorithmic_bytes(case, nlev)
+    abytes = comps * nlev * 4 * (nin + nout) + 9 * nout   # SURVEY.md 8(d) for this rank's share (algorithmic_bytes() when nothing is split)
     step_kern_ms = statistics.mean(step_ms)
     deg = {"nearest": 0, "linear": 1, "cubic": 3}[case.opts.get("interp_degree", "cubic")]
     if kms and (path & 10):
@@ -422,11 +443,13 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         roofline["traffic"] = tj.get("kernels", {}).get(roofline["kernel"], {}).get("dram_bytes_per_launch", tj.get("dram_bytes_per_launch"))
         roofline["traffic_source"] = tj.get("source")
 
+    if band_mode:
+        B.set_rows()
     del d_in, d_out, h_in, h_out, flush_buf
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": ms_per_step, "desc": desc, "nlev": nlev, "nin": nin, "nout": nout, "comps": comps, "e2e": e2e,
             "launches": int(launches), "gridset_build_ms": gridset_build_ms, "roofline": roofline, "sustained": sustained, "parity": par,
-            "collective": collective, "arith": arith, "l2": l2_note}
+            "collective": collective, "arith": arith, "l2": l2_note, "band_mode": band_mode}
 
 
 def sub_record(m):
@@ -551,11 +574,13 @@ def main():
             cpu_baseline = {"value": None, "unit": unit, "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
     line = {"metric": metric, "value": m["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.arith == 2 else "f64",
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong" if m["band_mode"] else "weak", "vs_baseline": None,
+            "dtype": "f32" if args.arith == 2 else "f64",
             "data": "synthetic",
             "config": {"workload": m["desc"], "levels_per_gpu": m["nlev"], "n_src": m["nin"], "n_out": m["nout"], "arith": args.arith,
                        "l2": m["l2"],
-                       "parallelism": "levels partitioned over %d GPU(s), replicated gridset" % world},
+                       "parallelism": ("output-row bands of one call split over %d GPU(s), replicated gridset and source field" if m["band_mode"] else
+                                       "levels partitioned over %d GPU(s), replicated gridset") % world},
             "e2e": m["e2e"],
             "gpu_launches": m["launches"],
             "gridset_build_ms": m["gridset_build_ms"],

@@ -143,6 +143,13 @@ int32_t c_ezb200_last_path(int32_t *nlist);
  * Returns -1 when the last launch was not timed. */
 int32_t c_ezb200_set_timing(int32_t on);
 int32_t c_ezb200_last_kernel_ms(float *ms, int32_t *tiles);
+/* Output-row band (multi-GPU split of a call with fewer fields than GPUs): until reset with (-1, -1) the calling
+ * thread's c_ezsint / c_ezuvint / *_batch calls produce only target rows [j0, j1) of the current set's target grid; the output
+ * arrays hold (j1 - j0) * ni points per field.  Bands made of whole 32-row tile rows (librmn_b200.sharding.row_band) keep the
+ * tile kernels and, stitched together, equal the full call bit for bit; any other band runs on the per-point kernel (same plans,
+ * fp32 difference form about the stencil centre: equal to the full call within rounding of the local variation).
+ * Not for 'U' targets. */
+int32_t c_ezb200_set_rows(int32_t j0, int32_t j1);
 int32_t c_ezb200_sync(void);
 const char *c_ezb200_version(void);
 

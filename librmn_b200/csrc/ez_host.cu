@@ -155,6 +155,7 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     cudaStream_t stream = 0;    // the stream every launch of this thread goes to (c_ezb200_set_stream; default: the legacy default stream)
     bool stream_user = false;   // set by the caller: never replaced
     cudaStream_t own_stream = nullptr;   // a private non-blocking stream for host-pointer calls of threads that never set one (HostCallStream)
+    int row0 = -1, row1 = -1;   // c_ezb200_set_rows: output-row band [row0, row1) of the target (multi-GPU split of one field); -1 = whole target
     int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
     bool timing = false;        // c_ezb200_set_timing: record events around the tile kernels of each interpolation launch
@@ -907,6 +908,23 @@ int check_degree() {
     return -1;
 }
 
+// Output-row band of the current session for target `out` (GPU g of G owns rows [g nj / G, (g + 1) nj / G) of a call
+// with fewer fields than GPUs; the caller's output arrays then hold (j1 - j0) * ni points per field).
+struct Band { int j0, j1; bool on; };
+Band band_of(const Grid &out) {
+    Band b{0, out.nj, false};
+    if (S.row0 >= 0 && S.row1 > S.row0) {
+        b.j0 = S.row0 < out.nj ? S.row0 : out.nj;
+        b.j1 = S.row1 < out.nj ? S.row1 : out.nj;
+        b.on = !(b.j0 == 0 && b.j1 == out.nj);
+    }
+    return b;
+}
+size_t out_points(const Grid &out) {
+    const Band b = band_of(out);
+    return (size_t)out.ni * (b.j1 - b.j0);
+}
+
 // zin/zout are DEVICE pointers here.  Returns 0, 2 (extrapolated) or -1.
 int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign,
              const float *polerow = nullptr) {
@@ -988,7 +1006,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
         }
     }
     // scattered ('Y' cloud) targets arrive in arbitrary order: the per-point kernel walks them sorted by source cell
-    if (!a.tiles && out.grtyp == 'Y' && a.o.arith >= 1 && a.npts >= 32768) {
+    if (!a.tiles && out.grtyp == 'Y' && a.o.arith >= 1 && a.npts >= 32768 && !band_of(out).on) {
         if (!gs->perm_tried) {
             gs->perm_tried = true;
             if (cudaMalloc((void **)&gs->d_perm, (size_t)a.npts * sizeof(int)) == cudaSuccess) {
@@ -1004,6 +1022,25 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             }
         }
         if (gs->d_perm) { a.list = gs->d_perm; a.nlist = a.npts; }
+    }
+    const Band band = band_of(out);
+    if (band.on) {
+        if (band.j1 <= band.j0) return rc;
+        const long off = (long)band.j0 * out.ni;
+        if (a.tiles && (band.j0 % 32) == 0 && ((band.j1 % 32) == 0 || band.j1 == out.nj)) {
+            // whole tile rows: the tile kernels and the list kernel skip what lies outside ; full-grid indexing lands in the band buffer
+            a.band_j0 = band.j0; a.band_j1 = band.j1;
+            a.zout = d_zout - off;
+        } else {
+            // any other band: the per-point kernel on the band's points (same plans, same arithmetic class as a full per-point call)
+            a.tiles = nullptr; a.tile_flags = nullptr; a.list = nullptr; a.nlist = 0;
+            a.ntiles_rowsep = a.ntiles_window = 0;
+            a.pc_idx = nullptr; a.pc_wx = a.pc_wy = nullptr; a.pc_sm1 = nullptr;
+            a.x += off; a.y += off;
+            if (a.zb) a.zb += off;
+            a.npts = (band.j1 - band.j0) * out.ni;
+            a.out_nj = band.j1 - band.j0;
+        }
     }
     S.last_path = a.tiles ? ((a.ntiles_window > 0 ? 2 : 0) | (a.nlist > 0 ? 4 : 0) | (a.ntiles_rowsep > 0 ? 8 : 0)) : 1;
     S.last_nlist = a.tiles ? a.nlist : 0;
@@ -1025,6 +1062,10 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     S.launches += ezk::interp(a, S.stream, timed ? &S.tev : nullptr, S.fork_ok ? &S.fork : nullptr);
     // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged
     if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
+        if (band.on) {
+            fprintf(stderr, "<ezb200> output-row bands are not supported for 'B' targets fed from a rotated source (pole rows are averaged over the whole row set)\n");
+            return -1;
+        }
         ezk::corrbgd(d_zout, out_stride, nfields, out.ni, out.nj, out.ig[0], S.stream);
         S.launches++;
     }
@@ -1035,6 +1076,10 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
 // c_ezyysint (ezyysint.c:26-242) + c_ezsint_orig, on device pointers
 int sint_any_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign) {
     const bool yyin = in.nsubgrids > 0, yyout = out.nsubgrids > 0;
+    if (yyout && S.row0 >= 0) {
+        fprintf(stderr, "<ezb200> output-row bands (c_ezb200_set_rows) are not supported for 'U' targets: split by sub-grid instead\n");
+        return -1;
+    }
     if (!yyin && !yyout) return sint_dev(out, in, d_zout, d_zin, nfields, in_stride, out_stride, vector, sym_sign);
     Grid *yin_out = yyout ? grid_of(out.subgrid[0]) : &out;
     Grid *yan_out = yyout ? grid_of(out.subgrid[1]) : nullptr;
@@ -1321,7 +1366,7 @@ int ezsint_n(float *zout, float *zin, int nfields) {
     if (!session_ok("c_ezsint")) return -1;
     if (nfields < 1) return -1;
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
-    const size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
+    const size_t nin = (size_t)in.ni * in.nj, nout = out_points(out);
     if (S.gdin == S.gdout) {   // ezsint.c:56-60
         Unlocked u;
         CUDA_OK(cudaMemcpyAsync(zout, zin, nin * nfields * sizeof(float), cudaMemcpyDefault, S.stream));
@@ -1357,18 +1402,25 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
         w.src = to_dev(in);
     }
     w.dst = to_dev(out);
-    w.lat = out.d_lat; w.lon = out.d_lon;
+    const Band band = band_of(out);
+    const long boff = band.on ? (long)band.j0 * out.ni : 0;   // output-row band: the per-point arrays of the target start at its first row
+    w.lat = out.d_lat + boff; w.lon = out.d_lon + boff;
+    if (w.zb) w.zb += boff;
     w.u = d_u; w.v = d_v;
     w.stride = stride;
     w.nfields = nfields;
-    w.npts = out.ni * out.nj;
+    w.npts = out.ni * (band.j1 - band.j0);
     w.mode = mode;
     if (mode == 0 && S.arith >= 1 && in.id != out.id) {   // cached rotation (ez_wind.cu); arith 0 keeps the reference's per-call evaluation
         Gset *gs = ensure_gset(out, in);
         if (gs && !gs->wrot_tried) {
             gs->wrot_tried = true;
-            if (cudaMalloc((void **)&gs->d_wrot, (size_t)w.npts * sizeof(float4)) == cudaSuccess) {
-                if (!ezk::wind_matrix(w, gs->d_wrot, S.stream)) { cudaFree(gs->d_wrot); gs->d_wrot = nullptr; }
+            WindArgs wf = w;   // the cached rotation always covers the whole target
+            wf.lat = out.d_lat; wf.lon = out.d_lon;
+            if (wf.zb) wf.zb -= boff;
+            wf.npts = out.ni * out.nj;
+            if (cudaMalloc((void **)&gs->d_wrot, (size_t)wf.npts * sizeof(float4)) == cudaSuccess) {
+                if (!ezk::wind_matrix(wf, gs->d_wrot, S.stream)) { cudaFree(gs->d_wrot); gs->d_wrot = nullptr; }
                 S.launches += 3;
             } else {
                 gs->d_wrot = nullptr;
@@ -1376,7 +1428,7 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
             }
         }
         if (gs && gs->d_wrot) {
-            ezk::wind_apply(gs->d_wrot, d_u, d_v, stride, nfields, w.npts, S.stream);
+            ezk::wind_apply(gs->d_wrot + boff, d_u, d_v, stride, nfields, w.npts, S.stream);
             S.launches++;
             CUDA_OK(cudaGetLastError());
             return 0;
@@ -1468,7 +1520,7 @@ int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields,
     if (!session_ok("c_ezuvint")) return -1;
     if (nfields < 1 || check_degree() < 0) return -1;
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
-    const size_t nin = (size_t)in.ni * in.nj, nout = (size_t)out.ni * out.nj;
+    const size_t nin = (size_t)in.ni * in.nj, nout = out_points(out);
     if (out.nsubgrids > 0 && in.nsubgrids > 0 && S.opt.use_1subgrid == 1) {
         fprintf(stderr, "<c_ezyyuvint> cannot use 1 subgrid to interpolate to a Yin-Yang grid  Aborting...\n");
         return -1;
@@ -1530,6 +1582,11 @@ void ftn_copy(char dst[32], const char *src, int32_t l) {
 // ===================================================================================================
 extern "C" {
 
+int32_t c_ezb200_set_rows(int32_t j0, int32_t j1) {
+    if (j0 < 0 || j1 <= j0) { S.row0 = S.row1 = -1; return 0; }
+    S.row0 = j0; S.row1 = j1;
+    return 0;
+}
 const char *c_ezb200_version(void) { return "ezb200 0.1 (sm_100a)"; }
 
 int32_t c_ezb200_set_stream(void *stream) {

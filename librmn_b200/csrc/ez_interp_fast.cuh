@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ Int
     const int t = blockIdx.x * TPB + threadIdx.x;
     if (t >= (a.list ? a.nlist : a.npts)) return;
     const int n = a.list ? a.list[t] : t;
+    if (a.band_j1 > 0 && a.list && (n < a.band_j0 * a.out_ni || n >= a.band_j1 * a.out_ni)) return;   // list points outside the output-row band
     const float px = a.x[n], py = a.y[n];
     const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
     const uint8_t zbits = a.use_zones ? (uint8_t)(bits & 0x1f) : (uint8_t)0;

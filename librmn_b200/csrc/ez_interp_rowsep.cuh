@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(RS_NTHR, EZ_ROWSEP_MINB) k_interp_rowsep(const
     extern __shared__ __align__(16) float smem[];
     const int by = remap_tile_row(blockIdx.y, gridDim.y);
     const int tile = by * gridDim.x + blockIdx.x;
+    if (a.band_j1 > 0 && (by * TO < a.band_j0 || by * TO >= a.band_j1)) return;   // output-row band: whole tile rows only
     const TileDesc td = a.tiles[tile];
     if (td.nfast == 0 || td.kind != 1) return;
     const int nstage_floats = RS_NSTAGE * LPS * a.tile_cap_rs;

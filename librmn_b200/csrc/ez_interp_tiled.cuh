@@ -539,11 +539,15 @@ template <int DEG>
 __global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int tile = a.win_tiles[blockIdx.x];
+    const int ntx = (a.out_ni + TO - 1) / TO;
+    if (a.band_j1 > 0) {   // output-row band: whole tile rows only (the host falls back to the per-point kernel otherwise)
+        const int row0 = (tile / ntx) * TO;
+        if (row0 < a.band_j0 || row0 >= a.band_j1) return;
+    }
     const TileDesc td = a.tiles[tile];
     // no zero fill: every cell a fast thread reads lies inside the field (k_tile_classify) and is written by the copies
     const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(smem);
     const bool fast = (a.tile_flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
-    const int ntx = (a.out_ni + TO - 1) / TO;
     const Quad q = quad_of_thread(tile % ntx, tile / ntx);
     if (td.panel) window_tile<DEG>(a.src2, a, td, q, fast, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32);
     else window_tile<DEG>(a.src, a, td, q, fast, a.zin, a.src.j2 - a.src.j1 + 1, smem32);

@@ -35,6 +35,9 @@ struct InterpArgs {
     int ntiles_rowsep, ntiles_window;
     const int *win_tiles;         // compacted list of the tiles the (persistent) window kernel owns, ntiles_window entries
     int rowsep_enable;            // classification only: allow tiles to be marked row-separable
+    // output-row band (multi-GPU split of one field): only target rows [band_j0, band_j1) are produced; zout then
+    // points band_j0 rows BEFORE the caller's band buffer, so that full-grid indexing lands in it.  0, 0 = the whole target.
+    int band_j0, band_j1;
     // plan cache of the tile plan (per target point: stencil origin, fp32 x / y weights, s = sum wx sum wy - 1), or nullptr:
     // the tile kernels then load 40 B per point instead of redoing the fp64 plan arithmetic in every launch
     const int *pc_idx;            // (r0 << 16) | c0
