@@ -57,6 +57,12 @@ int32_t c_ezgdef_fmem(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t 
                       float *ax, float *ay);                                       /* ref :28  (ezgdef_fmem.c:37) -> gdid */
 int32_t ezgdef_fmem_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
                      float *ax, float *ay, F2Cl lengrtyp, F2Cl lengrref);          /* ref :26 */
+int32_t c_ezgdef_fll(int32_t ni, int32_t nj, float *lat, float *lon);              /* ref :24  (ezgdef_fll.c:34) 'Y' cloud from lat/lon -> gdid */
+int32_t ezgdef_fll_(int32_t *ni, int32_t *nj, float *lat, float *lon);             /* ref :23 */
+int32_t c_gdgaxes(int32_t gdid, float *ax, float *ay);                             /* ref :96  (gdgaxes.c:31) */
+int32_t gdgaxes_(int32_t *gdid, float *ax, float *ay);                             /* ref :95 */
+int32_t c_gdxpncf(int32_t gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2);   /* ref :117 (gdxpncf.c:33) logical index range */
+int32_t gdxpncf_(int32_t *gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2);   /* ref :116 */
 int32_t c_ezgdef(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4,
                  float *ax, float *ay);                                            /* ref :15  (ezgdef.c:50); "FILE" sources -> -1 */
 int32_t ezgdef_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,

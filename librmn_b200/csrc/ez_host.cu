@@ -979,7 +979,10 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     a.out_nj = out.nj;
     // (fields of one call may come from different allocations -- the fused (u, v) launch --, so the first and the last are checked)
     const size_t field_bytes = (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)in.ni * in.nj) * sizeof(float);
-    if (ezk::tiled_eligible(a) && source_blocks_inside_allocation(d_zin, field_bytes) &&
+    // Few fields: a tile CTA's set-up (descriptor, copies in flight, plans) is not amortised and the per-point kernel wins
+    // (measured: C1 bilinear 1 field, C3 cubic 2 fields; profiles/r2_single_call.md).  EZB200_TILED_MIN_FIELDS overrides.
+    static const int tiled_min_fields = getenv("EZB200_TILED_MIN_FIELDS") ? atoi(getenv("EZB200_TILED_MIN_FIELDS")) : 1;
+    if (nfields >= tiled_min_fields && ezk::tiled_eligible(a) && source_blocks_inside_allocation(d_zin, field_bytes) &&
         (nfields == 1 || source_blocks_inside_allocation(d_zin + (long)(nfields - 1) * in_stride, field_bytes))) {
         TilePlan *tp = ensure_tileplan(*gs, a);
         if (!tp) return -1;
@@ -1657,6 +1660,47 @@ int32_t ezgdef_fmem_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t
     char t[2] = {grtyp[0], 0}, r[2] = {grref[0], 0};
     return c_ezgdef_fmem(*ni, *nj, t, r, *ig1, *ig2, *ig3, *ig4, ax, ay);
 }
+// ezgdef_fll.c:34-49: a 'Y' cloud of (lat, lon) points on an 'L' reference with lat0 = lon0 = 0, dlat = dlon = 1
+int32_t c_ezgdef_fll(int32_t ni, int32_t nj, float *lat, float *lon) {
+    int ig[4];
+    float xg[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+    ezh::cxgaig('L', ig, xg);
+    char t[2] = {'Y', 0}, r[2] = {'L', 0};
+    return c_ezgdef_fmem(ni, nj, t, r, ig[0], ig[1], ig[2], ig[3], lon, lat);
+}
+int32_t ezgdef_fll_(int32_t *ni, int32_t *nj, float *lat, float *lon) { return c_ezgdef_fll(*ni, *nj, lat, lon); }
+
+// gdgaxes.c:31-57: the positional axes the library copied at definition time (Z, #, G, Y grids)
+int32_t c_gdgaxes(int32_t gdid, float *ax, float *ay) {
+    Lock lk;
+    Grid *g = grid_of(gdid);
+    if (!g) return -1;
+    if (g->ax.empty() || g->ay.empty()) {
+        fprintf(stderr, "(gdgaxes) Erreur! A l'aide! Descripteurs manquants!\n");
+        return -1;
+    }
+    const size_t nix = g->grtyp == 'Y' ? (size_t)g->ni * g->nj : (size_t)g->ni;
+    const size_t njy = g->grtyp == 'Y' ? (size_t)g->ni * g->nj : (size_t)g->nj;
+    memcpy(ax, g->ax.data(), std::min(nix, g->ax.size()) * sizeof(float));
+    memcpy(ay, g->ay.data(), std::min(njy, g->ay.size()) * sizeof(float));
+    return 0;
+}
+int32_t gdgaxes_(int32_t *gdid, float *ax, float *ay) { c_gdgaxes(*gdid, ax, ay); return 0; }
+
+// gdxpncf.c:33-48: logical (expanded) index range of a grid
+int32_t c_gdxpncf(int32_t gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2) {
+    Lock lk;
+    Grid *g = grid_of(gdin);
+    if (!g) return -1;
+    if (g->nsubgrids > 0) {
+        fprintf(stderr, "<gdxpncf> This operation is not supported for 'U' grids.\n");
+        return -1;
+    }
+    *i1 = g->i1; *i2 = g->i2; *j1 = g->j1; *j2 = g->j2;
+    return 0;
+}
+int32_t gdxpncf_(int32_t *gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2) { return c_gdxpncf(*gdin, i1, i2, j1, j2); }
+
 int32_t c_ezqkdef(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit) {
     (void)iunit;
     char t = grtyp[0];

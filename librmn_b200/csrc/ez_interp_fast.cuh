@@ -334,6 +334,12 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
         }
         return;
     }
+    // outside the source with a constant extrapolation (ez_corrval.c:56-93: maximum / minimum / value; 0.0 for vectors, :64-67):
+    // a plain store -- a LAM source leaves a third of a larger target here (C3), and DEHORS excludes the polar zones (ez_defzones.c:88-109)
+    if (zbits == ZB_DEHORS && a.o.extrap >= EZ_MAXIMUM) {
+        for (int f = 0; f < nf; f++) zo[f * os] = (a.o.vector || !a.fs) ? 0.0f : a.fs[f0 + f].fudge;
+        return;
+    }
     // rare: a point in a polar / outside zone -- reference-order evaluators (ez_corrval semantics)
     const bool au_n = zbits & ZB_AU_NORD, au_s = zbits & ZB_AU_SUD, pole = zbits & (ZB_POLE_NORD | ZB_POLE_SUD);
     const bool irr = (g.grtyp == 'Z' || g.grtyp == 'G');
