@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libezb200.so")
-SOURCES = ["ez_host.cu", "ez_coord.cu", "ez_interp.cu", "ez_wind.cu"]
+SOURCES = ["ez_host.cu", "ez_coord.cu", "ez_interp.cu", "ez_wind.cu", "ez_cloud.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

@@ -76,6 +76,11 @@ struct Gset {   // _gridset, ez_def.h:148-166, device-resident
     int *d_perm = nullptr;      // 'Y' cloud targets: the points sorted by source cell (gather locality), built on first use
     bool perm_tried = false;
     int counts[6] = {0, 0, 0, 0, 0, 0};   // DEHORS, AU_NORD, AU_SUD, POLE_NORD, POLE_SUD, yang
+    // 'Y' cloud SOURCE (ez_cloud.cu; the reference's _ygrid, ez_def.h:136-146): k nearest source points and weights per target point
+    bool cloud = false;
+    int cloud_nw = 0;
+    int *d_cidx = nullptr, *d_cmask = nullptr;
+    float *d_cwts = nullptr;
 };
 
 struct Grid {   // _Grille, ez_def.h:196-222
@@ -666,8 +671,32 @@ Gset *ensure_gset(Grid &out, Grid &in) {
         gs->yy = true;
     } else {
         if (in.grtyp == 'Y') {
-            fprintf(stderr, "<ezb200> 'Y' cloud as a SOURCE grid is outside the hot-path scope (SURVEY.md 8f N2)\n");
-            return nullptr;
+            // ez_calcxy.c:99-128: no x, y for a cloud source (ez_calcxy_y never writes them): nearest points + weights instead
+            if (in.has_mask) {
+                fprintf(stderr, "<ezb200> masked 'Y' cloud sources (ez_calcxy_y_m) are not supported\n");
+                return nullptr;
+            }
+            if (ensure_latlon(in) < 0) return nullptr;
+            const int nw = S.opt.wgt_num;
+            if (nw < 1 || nw > 32) { fprintf(stderr, "<ezb200> weight_number %d is outside 1..32\n", nw); return nullptr; }
+            const size_t nsrc = (size_t)in.ni * in.nj;
+            if (cudaMalloc((void **)&gs->d_cidx, n * nw * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&gs->d_cwts, n * nw * sizeof(float)) != cudaSuccess ||
+                cudaMalloc((void **)&gs->d_cmask, n * sizeof(int)) != cudaSuccess) {
+                fprintf(stderr, "<ezb200> cudaMalloc failed for the cloud weights (%zu points x %d): %s\n", n, nw, cudaGetErrorString(cudaGetLastError()));
+                return nullptr;
+            }
+            cudaMemsetAsync(gs->d_x, 0, n * sizeof(float), S.stream);
+            cudaMemsetAsync(gs->d_y, 0, n * sizeof(float), S.stream);
+            cudaMemsetAsync(gs->d_zb, 0, n, S.stream);
+            if (!ezk::cloud_build(in.d_lat, in.d_lon, (int)nsrc, out.d_lat, out.d_lon, (int)n, nw, gs->d_cidx, gs->d_cwts, gs->d_cmask, S.stream)) {
+                fprintf(stderr, "<ezb200> cloud gridset build failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return nullptr;
+            }
+            S.launches += 8;
+            gs->cloud = true;
+            gs->cloud_nw = nw;
+            gs->built = true;
+            return gs;
         }
         if (ensure_device(in) < 0) return nullptr;
         int extrap = zone_extrap(in);
@@ -845,6 +874,10 @@ void free_gset(Gset &gs) {
     if (gs.d_zb) cudaFree(gs.d_zb);
     if (gs.d_perm) cudaFree(gs.d_perm);
     if (gs.d_wrot) cudaFree(gs.d_wrot);
+    if (gs.d_cidx) cudaFree(gs.d_cidx);
+    if (gs.d_cwts) cudaFree(gs.d_cwts);
+    if (gs.d_cmask) cudaFree(gs.d_cmask);
+    gs.d_cidx = gs.d_cmask = nullptr; gs.d_cwts = nullptr; gs.cloud = false;
     gs.d_wrot = nullptr; gs.wrot_tried = false;
     gs.d_perm = nullptr; gs.perm_tried = false;
     gs.d_x = gs.d_y = nullptr;
@@ -931,6 +964,24 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     if (check_degree() < 0) return -1;
     Gset *gs = ensure_gset(out, in);
     if (!gs) return -1;
+    if (gs->cloud) {
+        // gdinterp.c:207-235.  cloud_interp_alg = linear on a 2-D cloud would run ez_rgdint_1_nw on x, y that the reference never
+        // computes (ez_calcxy_y.inc:60-63 is commented out): undefined there, refused here.  Zones / polar correction do not apply:
+        // with polar_correction = yes the reference classifies the (uninitialised) x, y and, where they happen to be zero,
+        // overwrites the whole result with the extrapolation value -- callers of cloud sources switch it off.
+        if (in.ni > 1 && in.nj > 1 && S.opt.cld_interp_alg == EZ_LINEAR) {
+            fprintf(stderr, "<ezb200> cloud_interp_alg = linear on a 2-D 'Y' source reads coordinates the reference never computes; use distance\n");
+            return -1;
+        }
+        if (band_of(out).on) { fprintf(stderr, "<ezb200> output-row bands are not supported for 'Y' sources\n"); return -1; }
+        unsigned int *scr = (unsigned int *)S.st_scratch.get((size_t)nfields * 2 * sizeof(unsigned int));
+        if (!scr) return -1;
+        S.launches += ezk::cloud_apply(gs->d_cidx, gs->d_cwts, gs->d_cmask, gs->cloud_nw, d_zin, d_zout, in_stride, out_stride, nfields, in.ni * in.nj,
+                                       out.ni * out.nj, out.ni, S.opt.degre_extrap == EZ_VALUE, S.opt.valeur_extrap, scr, S.stream);
+        S.last_path = 1; S.last_nlist = 0;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     InterpArgs a;
     memset(&a, 0, sizeof(a));
     a.src = to_dev(in);
@@ -1378,10 +1429,17 @@ int ezsint_n(float *zout, float *zin, int nfields) {
     }
     const bool all_host = !is_device_ptr(zin) && !is_device_ptr(zout);
     HostCallStream hs(all_host);
-    if (nfields >= 2 && all_host) return ezsint_pipelined(out, in, zout, zin, nfields, nin, nout);
+    const bool cloud_src = in.grtyp == 'Y';
+    if (nfields >= 2 && all_host && !cloud_src) return ezsint_pipelined(out, in, zout, zin, nfields, nin, nout);
     Staged si, so;
     if (stage_in(si, S.st_in[0], zin, nin * nfields) < 0) return -1;
     if (stage_out(so, S.st_out[0], zout, nout * nfields) < 0) return -1;
+    if (cloud_src && so.host && nout > nin) {
+        // ez_applywgts leaves target points beyond the source's size untouched when they are masked out: they must read back
+        // as the caller had them
+        Unlocked u;
+        CUDA_OK(cudaMemcpyAsync(so.dev, zout, nout * nfields * sizeof(float), cudaMemcpyHostToDevice, S.stream));
+    }
     int rc = sint_any_dev(out, in, so.dev, si.dev, nfields, (long)nin, (long)nout, 0, 1);
     if (finish_out(so) < 0) return -1;
     return rc;
@@ -1542,7 +1600,7 @@ int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields,
     };
     const bool all_host = !is_device_ptr(uuin) && !is_device_ptr(vvin) && !is_device_ptr(uuout) && !is_device_ptr(vvout);
     HostCallStream hs(all_host);
-    if (all_host && nfields >= 2) {   // the level-chunk pipeline of the scalar path, two arrays each way
+    if (all_host && nfields >= 2 && in.grtyp != 'Y') {   // the level-chunk pipeline of the scalar path, two arrays each way
         PipeSpec p;
         p.narr = 2; p.in[0] = uuin; p.in[1] = vvin; p.out[0] = uuout; p.out[1] = vvout;
         p.nin = nin; p.nout = nout; p.nfields = nfields;
@@ -1551,6 +1609,11 @@ int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields,
     Staged su, sv, ou, ov;
     if (stage_in(su, S.st_in[0], uuin, nin * nfields) < 0 || stage_in(sv, S.st_in[1], vvin, nin * nfields) < 0) return -1;
     if (stage_out(ou, S.st_out[0], uuout, nout * nfields) < 0 || stage_out(ov, S.st_out[1], vvout, nout * nfields) < 0) return -1;
+    if (in.grtyp == 'Y' && nout > nin) {   // cloud sources leave masked-out target points beyond the source's size as the caller had them
+        Unlocked u;
+        if (ou.host) CUDA_OK(cudaMemcpyAsync(ou.dev, uuout, nout * nfields * sizeof(float), cudaMemcpyHostToDevice, S.stream));
+        if (ov.host) CUDA_OK(cudaMemcpyAsync(ov.dev, vvout, nout * nfields * sizeof(float), cudaMemcpyHostToDevice, S.stream));
+    }
     int rc = on_device(ou.dev, ov.dev, su.dev, sv.dev, nfields);
     if (rc < 0) return rc;
     if (finish_out(ou) < 0 || finish_out(ov) < 0) return -1;

@@ -107,6 +107,12 @@ void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
 void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *rowy, unsigned int *counters, cudaStream_t s);
 void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s);
 void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s);
+// 'Y' point clouds as a SOURCE (ez_cloud.cu): k nearest source points + inverse-square-distance weights per target point
+// ([nw][ndst] plane-major, 1-based indices, 0 = empty slot), and their application to nfields fields
+bool cloud_build(const float *src_lat, const float *src_lon, int nsrc, const float *dst_lat, const float *dst_lon, int ndst, int nw,
+                 int *idx, float *wts, int *mask, cudaStream_t s);
+int cloud_apply(const int *idx, const float *wts, const int *mask, int nw, const float *zin, float *zout, long in_stride, long out_stride, int nfields,
+                int nsrc, int ndst, int ni_dst, int use_value, float value, unsigned int *scratch, cudaStream_t s);
 // K19 integer mask transfer
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,
                    int linear, cudaStream_t s);

@@ -1469,8 +1469,120 @@ void qqq_ezsint_mask_(fint *mask_out, float *x, float *y, fint *ni_out_, fint *n
 /* ------------------------------------------------------------------ */
 /* off-path entry points: present so libezref.so links, abort if reached */
 /* ------------------------------------------------------------------ */
-void ez_applywgts_(void) { off_path("ez_applywgts"); }
-void ez_calcxy_y_(void) { off_path("ez_calcxy_y"); }
+
+/* ------------------------------------------------------------------ */
+/* 'Y' cloud SOURCES: ez_calcxy_y (k nearest + inverse-square-distance weights), ez_applywgts */
+/* ------------------------------------------------------------------ */
+/* src/interp/ez_calcxy_y.inc:1-94.  All arithmetic is default REAL (fp32).  x, y are never written (the call to
+ * inside_or_outside is commented out, :60-63).  tmp_idxs(16,2) is write-only.  maxloc(tmpwgts, 1) = FIRST slot of the maximum. */
+void ez_calcxy_y_(float *wts, fint *idxs, float *x, float *y, float *gdout_lat, float *gdout_lon, float *gdin_lat, float *gdin_lon,
+                  fint *masque, fint *ni_src_, fint *nj_src_, fint *ni_dst_, fint *nj_dst_, fint *num_wts_) {
+    (void)x; (void)y;
+    const long nsrc = (long)*ni_src_ * *nj_src_, ndst = (long)*ni_dst_ * *nj_dst_;
+    const int ni_src = *ni_src_, nw = *num_wts_;
+    float lon_min = gdin_lon[0], lon_max = gdin_lon[0], lat_min = gdin_lat[0], lat_max = gdin_lat[0];
+    for (long k = 1; k < nsrc; k++) {
+        if (gdin_lon[k] < lon_min) lon_min = gdin_lon[k];
+        if (gdin_lon[k] > lon_max) lon_max = gdin_lon[k];
+        if (gdin_lat[k] < lat_min) lat_min = gdin_lat[k];
+        if (gdin_lat[k] > lat_max) lat_max = gdin_lat[k];
+    }
+    for (long k = 0; k < ndst; k++) {
+        masque[k] = 1;
+        if (gdout_lon[k] < lon_min || gdout_lon[k] > lon_max || gdout_lat[k] < lat_min || gdout_lat[k] > lat_max) masque[k] = 0;
+    }
+    for (long k = 0; k < ndst * nw; k++) { wts[k] = 1.0e30f; idxs[k] = 0; }
+    float *tmpwgts = (float *)malloc(sizeof(float) * (size_t)nw);
+    for (long k = 0; k < ndst; k++) {
+        if (masque[k] == 0) continue;
+        for (int n = 0; n < nw; n++) tmpwgts[n] = 1.0e30f;
+        int locmax = 0;
+        int point_found = 0;
+        const float lo = gdout_lon[k], la = gdout_lat[k];
+        for (long s = 0; s < nsrc; s++) {   /* jj outer, ii inner == increasing linear index */
+            float rx = lo - gdin_lon[s];
+            const float ry = la - gdin_lat[s];
+            if (fabsf(rx) > 180.0f) rx = fabsf(fabsf(rx) - 360.0f);
+            if (fabsf(ry) < 10.0f && fabsf(rx) < 10.0f) {
+                const float dist = rx * rx + ry * ry;
+                point_found = 1;
+                if (dist < tmpwgts[locmax]) {
+                    tmpwgts[locmax] = dist;
+                    idxs[k + (long)locmax * ndst] = (fint)(s + 1);   /* ii + (jj-1)*ni_src */
+                    locmax = 0;
+                    for (int n = 1; n < nw; n++)
+                        if (tmpwgts[n] > tmpwgts[locmax]) locmax = n;
+                }
+            }
+        }
+        (void)ni_src;
+        if (!point_found) masque[k] = 0;
+        if (masque[k] == 1) {
+            for (int n = 0; n < nw; n++) wts[k + (long)n * ndst] = tmpwgts[n];
+            if (wts[k] > 6371000.0f) {
+                for (int n = 0; n < nw; n++) wts[k + (long)n * ndst] = 1.0e30f;
+                masque[k] = 0;
+            } else {
+                float total_wgt = 0.0f;
+                for (int n = 0; n < nw; n++) {
+                    float w = wts[k + (long)n * ndst];
+                    w = fmaxf(w, 1.0e-10f);
+                    wts[k + (long)n * ndst] = 1.0f / w;
+                }
+                for (int n = 0; n < nw; n++) total_wgt = total_wgt + wts[k + (long)n * ndst];
+                for (int n = 0; n < nw; n++) wts[k + (long)n * ndst] = wts[k + (long)n * ndst] / total_wgt;
+            }
+        }
+    }
+    free(tmpwgts);
+}
+
+/* the reference's own C option getters (src/interp/ezgetopt.c, ezgetval.c), present when linked into libezref.so */
+extern int32_t c_ezgetopt(char *option, char *value) __attribute__((weak));
+extern int32_t c_ezgetval(char *option, float *value) __attribute__((weak));
+
+/* src/interp/ez_applywgts.inc:1-48, quirks kept:
+ *   - outfld is DECLARED with ni_src*nj_src elements (:7): the whole-array assignments `outfld = xtrapval` / `outfld = rmin`
+ *     (:27,:33) fill only that many; target points beyond keep what the caller's array held when their mask is 0;
+ *   - j = 1 + k / ni_dst (:38) is one row too far for the last column (k a multiple of ni_dst): those points read the
+ *     weight / index lists of linear element k - 1 + ni_dst of the same plane (running into the next plane on the last row). */
+void ez_applywgts_(float *outfld, float *wts, fint *idxs, float *infld, float *x, float *y, fint *masque, fint *ni_src_, fint *nj_src_,
+                   fint *ni_dst_, fint *nj_dst_, fint *n_wts_) {
+    (void)x; (void)y;
+    const long nsrc = (long)*ni_src_ * *nj_src_, ndst = (long)*ni_dst_ * *nj_dst_;
+    const int ni_dst = *ni_dst_, nw = *n_wts_;
+    char xtrapopt[64] = "maximum";
+    float xtrapval = 0.0f;
+    if (c_ezgetopt) { char o[] = "extrap_degree"; c_ezgetopt(o, xtrapopt); }
+    if (c_ezgetval) { char o[] = "extrap_value"; c_ezgetval(o, &xtrapval); }
+    float fill;
+    if (strncmp(xtrapopt, "value", 5) == 0) {
+        fill = xtrapval;
+    } else {
+        float rmin = infld[0], rmax = infld[0];
+        for (long k = 1; k < nsrc; k++) {
+            if (infld[k] < rmin) rmin = infld[k];
+            if (infld[k] > rmax) rmax = infld[k];
+        }
+        rmin = rmin - 0.1f * (rmax - rmin);
+        fill = rmin;
+    }
+    /* (sic) the declared extent, not the target's.  With more source than target points the reference writes past the end of
+     * the caller's output array; the restatement stops at the target's size instead of corrupting the heap. */
+    for (long k = 0; k < (nsrc < ndst ? nsrc : ndst); k++) outfld[k] = fill;
+    for (long k = 1; k <= ndst; k++) {
+        const long i = ((k - 1) % ni_dst) + 1, j = 1 + k / ni_dst;
+        if (masque[k - 1] == 1) {
+            outfld[k - 1] = 0.0f;
+            for (int n = 1; n <= nw; n++) {
+                const long e = (i - 1) + (j - 1) * (long)ni_dst + (long)(n - 1) * ndst;
+                if (e >= ndst * (long)nw) break;   /* (past the end of the arrays: undefined in the reference) */
+                if (idxs[e] < 1) break;
+                outfld[k - 1] = outfld[k - 1] + wts[e] * infld[idxs[e] - 1];
+            }
+        }
+    }
+}
 void ez_calcxy_y_m_(void) { off_path("ez_calcxy_y_m"); }
 void ez_avg_(void) { off_path("ez_avg"); }
 void ez_avg_sph_(void) { off_path("ez_avg_sph"); }
