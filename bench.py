@@ -350,6 +350,22 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
         del p_in, p_out
         phase("e2e pageable")
 
+    # ---- one process, every visible GPU: the same host-array call fanned out by the library (c_ezb200_set_devices) ----
+    ndev_vis = torch.cuda.device_count()
+    if world == 1 and ndev_vis > 1 and nlev >= 2 * ndev_vis and not band_mode:
+        for nd in sorted({2, ndev_vis}):
+            if nd > ndev_vis:
+                continue
+            used = B.set_devices(nd)
+            try:
+                fo_ms = time_host(h_in, h_out, e2e_steps)
+            finally:
+                B.set_devices(1)
+            e2e.setdefault("fanout", {})["%d_gpus" % used] = {"value": nout_full * nlev / (fo_ms * 1e-3), "unit": "points/s", "ms_per_step": fo_ms,
+                                                              "host_memory": "pinned", "what": "ONE process, one c_ezsint_batch call on host arrays, "
+                                                              "levels cut into %d blocks by the library, one gridset replica per device" % used}
+        phase("e2e fan-out")
+
     # ---- optional collective: gather every rank's level block on every rank (NCCL all-gather over NVLink) ----
     collective = None
     if gather and world > 1:

@@ -156,6 +156,12 @@ int32_t c_ezb200_last_kernel_ms(float *ms, int32_t *tiles);
  * fp32 difference form about the stencil centre: equal to the full call within rounding of the local variation).
  * Not for 'U' targets. */
 int32_t c_ezb200_set_rows(int32_t j0, int32_t j1);
+/* One process, several GPUs: from now on the calling thread's c_ezsint_batch / c_ezuvint_batch calls on HOST arrays with at least
+ * 2 n fields are cut into n contiguous blocks of fields, one per CUDA device (the current device and the next visible ones); each
+ * device holds its own replica of the gridset (built on its first call) and moves its own block over its own PCIe link.
+ * Returns the number of devices that will be used (clamped to the visible ones); 1 = single device (default).
+ * The environment variable EZB200_DEVICES sets the initial value for every thread. */
+int32_t c_ezb200_set_devices(int32_t n);
 int32_t c_ezb200_sync(void);
 const char *c_ezb200_version(void);
 

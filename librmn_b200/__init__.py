@@ -101,6 +101,7 @@ class EzLib:
             L.c_ezb200_last_path.argtypes = [C.POINTER(_i32)]
             L.c_ezb200_set_timing.argtypes = [_i32]
             L.c_ezb200_set_rows.argtypes = [_i32, _i32]
+            L.c_ezb200_set_devices.argtypes = [_i32]
             L.c_ezb200_last_kernel_ms.argtypes = [C.POINTER(C.c_float), C.POINTER(_i32)]
 
     # ---- descriptors -------------------------------------------------------------------------
@@ -263,6 +264,10 @@ class EzLib:
 
     def set_arith(self, mode):
         return self.lib.c_ezb200_set_arith(mode)
+
+    def set_devices(self, n=1):
+        """Fan host-array batch calls of this thread out over n CUDA devices (one gridset replica each); returns the number used."""
+        return self.lib.c_ezb200_set_devices(n)
 
     def set_rows(self, j0=-1, j1=-1):
         """Output-row band [j0, j1) of the target for this thread's following calls; no arguments = whole target again."""

@@ -18,6 +18,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -100,11 +101,19 @@ struct Grid {   // _Grille, ez_def.h:196-222
     int mymaskgrid = -1, mi0 = 0, mi1 = 0, mj0 = 0, mj1 = 0;
     std::vector<int> mask;
     bool has_mask = false;
-    // device side
-    int device = -1;
-    float *d_ax = nullptr, *d_ay = nullptr, *d_cx = nullptr, *d_cy = nullptr;
-    float *d_lat = nullptr, *d_lon = nullptr;   // flag LAT
-    std::map<int, std::unique_ptr<Gset>> gsets; // keyed by gdin (this grid is the target)
+    // device side: one replica per CUDA device that has used the grid (the registry and the descriptors above are shared; a call
+    // works on the replica of the calling thread's current device -- one process per GPU sees exactly one, a process that fans
+    // a multi-level call out over the GPUs of a box (c_ezb200_set_devices) builds one per device, deterministically identical)
+    struct DevState {
+        bool ready = false;   // axes and Newton tables uploaded
+        float *d_ax = nullptr, *d_ay = nullptr, *d_cx = nullptr, *d_cy = nullptr;
+        float *d_lat = nullptr, *d_lon = nullptr;   // flag LAT
+        std::map<int, std::unique_ptr<Gset>> gsets; // keyed by gdin (this grid is the target)
+    };
+    static constexpr int MAX_DEV = 16;
+    DevState dv[MAX_DEV];
+    DevState &ds();
+    const DevState &ds() const;
 };
 
 // One mutex guards the registry, the gridsets and everything built into them (tile plans, plan caches, rotations).  The
@@ -115,8 +124,18 @@ struct Grid {   // _Grille, ez_def.h:196-222
 // synchronisation -- so that the per-thread streams of concurrent callers overlap (Unlocked below).
 std::recursive_mutex g_mtx;
 thread_local int t_lock_depth = 0;
+thread_local int t_dev = 0;   // the calling thread's current CUDA device, refreshed whenever an entry point takes the lock
+Grid::DevState &Grid::ds() { return dv[t_dev]; }
+const Grid::DevState &Grid::ds() const { return dv[t_dev]; }
 struct Lock {
-    Lock() { g_mtx.lock(); t_lock_depth++; }
+    Lock() {
+        g_mtx.lock();
+        if (t_lock_depth++ == 0) {
+            int d = 0;
+            if (cudaGetDevice(&d) != cudaSuccess) { (void)cudaGetLastError(); d = 0; }
+            t_dev = (d >= 0 && d < Grid::MAX_DEV) ? d : 0;
+        }
+    }
     ~Lock() { t_lock_depth--; g_mtx.unlock(); }
     Lock(const Lock &) = delete;
     Lock &operator=(const Lock &) = delete;
@@ -154,12 +173,19 @@ struct DevBuf {
     }
 };
 
+inline int env_devices() {
+    const char *e = getenv("EZB200_DEVICES");
+    const int n = e ? atoi(e) : 1;
+    return n < 1 ? 1 : n;
+}
+
 struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus per-thread CUDA state
     int gdin = -1, gdout = -1;
     Options opt;
     cudaStream_t stream = 0;    // the stream every launch of this thread goes to (c_ezb200_set_stream; default: the legacy default stream)
     bool stream_user = false;   // set by the caller: never replaced
     cudaStream_t own_stream = nullptr;   // a private non-blocking stream for host-pointer calls of threads that never set one (HostCallStream)
+    int devices = env_devices();   // c_ezb200_set_devices (initial value: EZB200_DEVICES, default 1): GPUs a host-pointer multi-field call of this thread is fanned out over
     int row0 = -1, row1 = -1;   // c_ezb200_set_rows: output-row band [row0, row1) of the target (multi-GPU split of one field); -1 = whole target
     int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
@@ -528,21 +554,16 @@ void gdef_yymask(Grid &sub) {
 // device mirrors
 // ---------------------------------------------------------------------------------------------------
 int ensure_device(Grid &g) {
-    int dev = 0;
-    CUDA_OK(cudaGetDevice(&dev));
-    if (g.device == dev) return 0;
-    if (g.device >= 0 && g.device != dev) {
-        fprintf(stderr, "<ezb200> grid %d was built on CUDA device %d but the current device is %d (one process per GPU)\n", g.id, g.device, dev);
-        return -1;
-    }
-    auto up = [&](float **d, const std::vector<float> &h) -> int {
+    Grid::DevState &d = g.ds();
+    if (d.ready) return 0;
+    auto up = [&](float **dp, const std::vector<float> &h) -> int {
         if (h.empty()) return 0;
-        CUDA_OK(cudaMalloc((void **)d, h.size() * sizeof(float)));
-        CUDA_OK(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc((void **)dp, h.size() * sizeof(float)));
+        CUDA_OK(cudaMemcpy(*dp, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
         return 0;
     };
-    if (up(&g.d_ax, g.ax) < 0 || up(&g.d_ay, g.ay) < 0 || up(&g.d_cx, g.ncx) < 0 || up(&g.d_cy, g.ncy) < 0) return -1;
-    g.device = dev;
+    if (up(&d.d_ax, g.ax) < 0 || up(&d.d_ay, g.ay) < 0 || up(&d.d_cx, g.ncx) < 0 || up(&d.d_cy, g.ncy) < 0) return -1;
+    d.ready = true;
     return 0;
 }
 
@@ -563,30 +584,30 @@ GridDev to_dev(const Grid &g) {
         d.ig[k] = g.ig[k]; d.igref[k] = g.igref[k]; d.xg[k] = g.xg[k]; d.xgref[k] = g.xgref[k]; d.llp[k] = g.llp[k]; d.xyp[k] = g.xyp[k];
     }
     for (int k = 0; k < 9; k++) { d.r[k] = g.r[k]; d.ri[k] = g.ri[k]; }
-    d.ax = g.d_ax; d.ay = g.d_ay; d.cx = g.d_cx; d.cy = g.d_cy;
+    d.ax = g.ds().d_ax; d.ay = g.ds().d_ay; d.cx = g.ds().d_cx; d.cy = g.ds().d_cy;
     return d;
 }
 
 // ez_calclatlon, ez_calclatlon.c:30 (flag LAT): device-resident lat/lon of every grid point
 int ensure_latlon(Grid &g) {
-    if (g.d_lat) return 0;
+    if (g.ds().d_lat) return 0;
     if (g.grtyp == 'Y' && (g.grref == 'N' || g.grref == 'S' || g.grref == 'E')) {
         fprintf(stderr, "<ez_calclatlon> Operation not supported - Y grid on %c Grid\n", g.grref);
         return -1;
     }
     if (ensure_device(g) < 0) return -1;
     size_t n = (size_t)g.ni * g.nj;
-    if (dev_alloc(&g.d_lat, n) < 0) { g.d_lat = nullptr; return -1; }
-    if (dev_alloc(&g.d_lon, n) < 0) { cudaFree(g.d_lat); g.d_lat = g.d_lon = nullptr; return -1; }
-    ezk::calclatlon(to_dev(g), g.d_lat, g.d_lon, (int)n, S.stream);
+    if (dev_alloc(&g.ds().d_lat, n) < 0) { g.ds().d_lat = nullptr; return -1; }
+    if (dev_alloc(&g.ds().d_lon, n) < 0) { cudaFree(g.ds().d_lat); g.ds().d_lat = g.ds().d_lon = nullptr; return -1; }
+    ezk::calclatlon(to_dev(g), g.ds().d_lat, g.ds().d_lon, (int)n, S.stream);
     S.launches++;
     // cached state shared by every session: complete before it is visible to other threads' streams
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(S.stream);
     if (e != cudaSuccess) {
         fprintf(stderr, "<ezb200> lat/lon build failed: %s\n", cudaGetErrorString(e));
-        cudaFree(g.d_lat); cudaFree(g.d_lon);
-        g.d_lat = g.d_lon = nullptr;
+        cudaFree(g.ds().d_lat); cudaFree(g.ds().d_lon);
+        g.ds().d_lat = g.ds().d_lon = nullptr;
         return -1;
     }
     return 0;
@@ -637,7 +658,7 @@ void free_gset(Gset &gs);
 // The gridset build: ez_calcxy (ez_calcxy.c:28) + ez_defzones (ez_defzones.c:25) for a plain source,
 // c_ezyy_calcxy (ezyy_calcxy.c:28) for a 'U' source.  Runs once per (gdout, gdin); results stay in HBM.
 Gset *ensure_gset(Grid &out, Grid &in) {
-    auto &slot = out.gsets[in.id];
+    auto &slot = out.ds().gsets[in.id];
     if (!slot) {
         slot = std::make_unique<Gset>();
         slot->gdin = in.id;
@@ -665,7 +686,7 @@ Gset *ensure_gset(Grid &out, Grid &in) {
         if (!yin || !yan || !mk) return nullptr;
         if (ensure_device(*yin) < 0 || ensure_device(*yan) < 0 || ensure_device(*mk) < 0) return nullptr;
         // the mask is produced under the caller's current polar_correction (ezyymint.c:56-64)
-        ezk::yy_calcxy(to_dev(*mk), to_dev(*yin), to_dev(*yan), S.opt.polar_correction == 1, out.d_lat, out.d_lon, gs->d_x, gs->d_y, gs->d_zb,
+        ezk::yy_calcxy(to_dev(*mk), to_dev(*yin), to_dev(*yan), S.opt.polar_correction == 1, out.ds().d_lat, out.ds().d_lon, gs->d_x, gs->d_y, gs->d_zb,
                        d_counts, (int)n, S.stream);
         S.launches++;
         gs->yy = true;
@@ -688,7 +709,7 @@ Gset *ensure_gset(Grid &out, Grid &in) {
             cudaMemsetAsync(gs->d_x, 0, n * sizeof(float), S.stream);
             cudaMemsetAsync(gs->d_y, 0, n * sizeof(float), S.stream);
             cudaMemsetAsync(gs->d_zb, 0, n, S.stream);
-            if (!ezk::cloud_build(in.d_lat, in.d_lon, (int)nsrc, out.d_lat, out.d_lon, (int)n, nw, gs->d_cidx, gs->d_cwts, gs->d_cmask, S.stream)) {
+            if (!ezk::cloud_build(in.ds().d_lat, in.ds().d_lon, (int)nsrc, out.ds().d_lat, out.ds().d_lon, (int)n, nw, gs->d_cidx, gs->d_cwts, gs->d_cmask, S.stream)) {
                 fprintf(stderr, "<ezb200> cloud gridset build failed: %s\n", cudaGetErrorString(cudaGetLastError()));
                 return nullptr;
             }
@@ -713,7 +734,7 @@ Gset *ensure_gset(Grid &out, Grid &in) {
         }
         // lon is mutated in place by the A/B/L and Z-on-L coordinate routes
         int wb = (in.grtyp == 'A' || in.grtyp == 'B' || in.grtyp == 'L' || ((in.grtyp == 'Z' || in.grtyp == '#' || in.grtyp == 'G') && in.grref == 'L'));
-        ezk::calcxy(to_dev(in), in.nj, out.d_lat, out.d_lon, wb, gs->d_x, gs->d_y, gs->d_zb, 1, extrap, ypn, yps, d_counts, (int)n, S.stream);
+        ezk::calcxy(to_dev(in), in.nj, out.ds().d_lat, out.ds().d_lon, wb, gs->d_x, gs->d_y, gs->d_zb, 1, extrap, ypn, yps, d_counts, (int)n, S.stream);
         S.launches++;
     }
     unsigned int hc[8];
@@ -1415,6 +1436,133 @@ int ezsint_pipelined(Grid &out, Grid &in, float *zout, const float *zin, int nfi
     });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// one process, several GPUs: a host-pointer call over many fields is cut into contiguous blocks of fields, one per device
+// ---------------------------------------------------------------------------------------------------
+// BASELINE.json north_star: "multi-field and multi-level calls are partitioned across the 8 GPUs of one box by level ... each GPU
+// holding a replicated gset".  One persistent worker thread per extra device (its thread-local Session owns that device's
+// streams, staging buffers and pinned ring); the calling thread keeps the block of its own current device.  Every block runs
+// the ordinary single-device path (the level-chunk pipeline above), so each device's PCIe link carries its own share.
+class DeviceWorkers {
+    struct Worker {
+        int dev = 0;
+        std::thread th;
+        std::mutex m;
+        std::condition_variable cv;
+        std::function<int()> job;
+        bool has_job = false, done = true;
+        int rc = 0;
+    };
+    std::vector<std::unique_ptr<Worker>> w;   // index = CUDA device ordinal
+    std::mutex m;
+
+    static void run(Worker *k) {
+        cudaSetDevice(k->dev);
+        for (;;) {
+            std::function<int()> job;
+            {
+                std::unique_lock<std::mutex> lk(k->m);
+                k->cv.wait(lk, [&] { return k->has_job; });
+                job = std::move(k->job);
+                k->has_job = false;
+            }
+            const int rc = job();
+            {
+                std::lock_guard<std::mutex> lk(k->m);
+                k->rc = rc;
+                k->done = true;
+            }
+            k->cv.notify_all();
+        }
+    }
+
+public:
+    void submit(int dev, std::function<int()> job) {
+        Worker *k;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            if ((int)w.size() <= dev) w.resize(dev + 1);
+            if (!w[dev]) {
+                w[dev] = std::make_unique<Worker>();
+                w[dev]->dev = dev;
+                w[dev]->th = std::thread(run, w[dev].get());
+                w[dev]->th.detach();
+            }
+            k = w[dev].get();
+        }
+        {
+            std::lock_guard<std::mutex> lk(k->m);
+            k->job = std::move(job);
+            k->has_job = true;
+            k->done = false;
+        }
+        k->cv.notify_all();
+    }
+    int wait(int dev) {
+        Worker *k;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            k = w[dev].get();
+        }
+        std::unique_lock<std::mutex> lk(k->m);
+        k->cv.wait(lk, [&] { return k->done; });
+        return k->rc;
+    }
+};
+DeviceWorkers &g_workers = *new DeviceWorkers;   // never destroyed (threads wait on its condition variables until the process ends)
+
+int visible_devices() {
+    static int n = -1;
+    if (n < 0) {
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); n = 1; }
+        if (n > Grid::MAX_DEV) n = Grid::MAX_DEV;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
+int ezsint_n(float *zout, float *zin, int nfields);
+int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields, int mode);
+
+// Returns -2 when the call is not fanned out (the caller then runs the single-device path), else the reference's return code.
+// block(f0, nf) runs fields [f0, f0 + nf) on the CURRENT thread and device.
+int fan_out(int nfields, bool all_host, const std::function<int(int, int)> &block) {
+    const int ndev = std::min(S.devices, visible_devices());
+    if (ndev <= 1 || !all_host || nfields < 2 * ndev || S.row0 >= 0) return -2;
+    // this thread's session, as the workers must see it
+    const int gdin = S.gdin, gdout = S.gdout, arith = S.arith;
+    const Options opt = S.opt;
+    const int dev0 = t_dev;
+    std::vector<int> devs;
+    devs.push_back(dev0);
+    for (int d = 0; d < visible_devices() && (int)devs.size() < ndev; d++)
+        if (d != dev0) devs.push_back(d);
+    Unlocked u;   // the blocks take the registry lock themselves
+    std::vector<std::pair<int, int>> span(devs.size());
+    for (size_t k = 0; k < devs.size(); k++) {
+        const int base = nfields / (int)devs.size(), rem = nfields % (int)devs.size();
+        const int lo = (int)k * base + std::min((int)k, rem);
+        span[k] = {lo, base + ((int)k < rem ? 1 : 0)};
+    }
+    for (size_t k = 1; k < devs.size(); k++) {
+        const int lo = span[k].first, nf = span[k].second;
+        g_workers.submit(devs[k], [=, &block]() -> int {
+            S.gdin = gdin; S.gdout = gdout; S.arith = arith; S.opt = opt; S.devices = 1; S.row0 = S.row1 = -1;
+            return block(lo, nf);
+        });
+    }
+    const int saved = S.devices;
+    S.devices = 1;
+    int rc = block(span[0].first, span[0].second);
+    S.devices = saved;
+    for (size_t k = 1; k < devs.size(); k++) {
+        const int r = g_workers.wait(devs[k]);
+        if (r < 0 || rc < 0) rc = -1;
+        else if (r > rc) rc = r;
+    }
+    return rc;
+}
+
 int ezsint_n(float *zout, float *zin, int nfields) {
     Lock lk;
     if (!session_ok("c_ezsint")) return -1;
@@ -1428,8 +1576,12 @@ int ezsint_n(float *zout, float *zin, int nfields) {
         return 1;
     }
     const bool all_host = !is_device_ptr(zin) && !is_device_ptr(zout);
-    HostCallStream hs(all_host);
     const bool cloud_src = in.grtyp == 'Y';
+    if (S.devices > 1 && !cloud_src) {
+        const int r = fan_out(nfields, all_host, [&](int f0, int nf) { return ezsint_n(zout + (size_t)f0 * nout, zin + (size_t)f0 * nin, nf); });
+        if (r != -2) return r;
+    }
+    HostCallStream hs(all_host);
     if (nfields >= 2 && all_host && !cloud_src) return ezsint_pipelined(out, in, zout, zin, nfields, nin, nout);
     Staged si, so;
     if (stage_in(si, S.st_in[0], zin, nin * nfields) < 0) return -1;
@@ -1465,7 +1617,7 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
     w.dst = to_dev(out);
     const Band band = band_of(out);
     const long boff = band.on ? (long)band.j0 * out.ni : 0;   // output-row band: the per-point arrays of the target start at its first row
-    w.lat = out.d_lat + boff; w.lon = out.d_lon + boff;
+    w.lat = out.ds().d_lat + boff; w.lon = out.ds().d_lon + boff;
     if (w.zb) w.zb += boff;
     w.u = d_u; w.v = d_v;
     w.stride = stride;
@@ -1477,7 +1629,7 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
         if (gs && !gs->wrot_tried) {
             gs->wrot_tried = true;
             WindArgs wf = w;   // the cached rotation always covers the whole target
-            wf.lat = out.d_lat; wf.lon = out.d_lon;
+            wf.lat = out.ds().d_lat; wf.lon = out.ds().d_lon;
             if (wf.zb) wf.zb -= boff;
             wf.npts = out.ni * out.nj;
             if (cudaMalloc((void **)&gs->d_wrot, (size_t)wf.npts * sizeof(float4)) == cudaSuccess) {
@@ -1599,6 +1751,12 @@ int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields,
         return uvint_dev(out, in, d_uo, d_vo, d_ui, d_vi, nf, (long)nin, (long)nout, mode);
     };
     const bool all_host = !is_device_ptr(uuin) && !is_device_ptr(vvin) && !is_device_ptr(uuout) && !is_device_ptr(vvout);
+    if (S.devices > 1 && in.grtyp != 'Y') {
+        const int r = fan_out(nfields, all_host, [&](int f0, int nf) {
+            return ezuvint_n(uuout + (size_t)f0 * nout, vvout + (size_t)f0 * nout, uuin + (size_t)f0 * nin, vvin + (size_t)f0 * nin, nf, mode);
+        });
+        if (r != -2) return r;
+    }
     HostCallStream hs(all_host);
     if (all_host && nfields >= 2 && in.grtyp != 'Y') {   // the level-chunk pipeline of the scalar path, two arrays each way
         PipeSpec p;
@@ -1648,6 +1806,11 @@ void ftn_copy(char dst[32], const char *src, int32_t l) {
 // ===================================================================================================
 extern "C" {
 
+int32_t c_ezb200_set_devices(int32_t n) {
+    if (n < 1) n = 1;
+    S.devices = std::min(n, visible_devices());
+    return S.devices;
+}
 int32_t c_ezb200_set_rows(int32_t j0, int32_t j1) {
     if (j0 < 0 || j1 <= j0) { S.row0 = S.row1 = -1; return 0; }
     S.row0 = j0; S.row1 = j1;
@@ -1850,15 +2013,19 @@ int32_t c_gdrls(int32_t gdin) {   // gdrls.c:34-90
     if (!g) return 0;
     if (g->access_count > 0) g->access_count--;
     if (g->access_count == 0) {
-        for (auto &kv : g->gsets) free_gset(*kv.second);
-        g->gsets.clear();
-        for (auto &up : g_grids)   // gridsets that use this grid as their source
-            if (up && up->alive) {
-                auto it = up->gsets.find(gdin);
-                if (it != up->gsets.end()) { free_gset(*it->second); up->gsets.erase(it); }
-            }
-        float **ptrs[] = {&g->d_ax, &g->d_ay, &g->d_cx, &g->d_cy, &g->d_lat, &g->d_lon};
-        for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+        for (int dvi = 0; dvi < Grid::MAX_DEV; dvi++) {   // every device replica (cudaFree takes pointers of any device)
+            Grid::DevState &d = g->dv[dvi];
+            for (auto &kv : d.gsets) free_gset(*kv.second);
+            d.gsets.clear();
+            for (auto &up : g_grids)   // gridsets that use this grid as their source
+                if (up && up->alive) {
+                    auto it = up->dv[dvi].gsets.find(gdin);
+                    if (it != up->dv[dvi].gsets.end()) { free_gset(*it->second); up->dv[dvi].gsets.erase(it); }
+                }
+            float **ptrs[] = {&d.d_ax, &d.d_ay, &d.d_cx, &d.d_cy, &d.d_lat, &d.d_lon};
+            for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+            d.ready = false;
+        }
         g->alive = false;
     }
     return 0;
@@ -1931,8 +2098,8 @@ int32_t c_gdll(int32_t gdid, float *lat, float *lon) {   // gdll.c:25-73
     }
     if (ensure_latlon(*g) < 0) return -1;
     size_t n = (size_t)g->ni * g->nj;
-    CUDA_OK(cudaMemcpyAsync(lat, g->d_lat, n * sizeof(float), cudaMemcpyDefault, S.stream));
-    CUDA_OK(cudaMemcpyAsync(lon, g->d_lon, n * sizeof(float), cudaMemcpyDefault, S.stream));
+    CUDA_OK(cudaMemcpyAsync(lat, g->ds().d_lat, n * sizeof(float), cudaMemcpyDefault, S.stream));
+    CUDA_OK(cudaMemcpyAsync(lon, g->ds().d_lon, n * sizeof(float), cudaMemcpyDefault, S.stream));
     CUDA_OK(cudaStreamSynchronize(S.stream));
     return 0;
 }
@@ -2263,7 +2430,7 @@ int32_t c_ezdefset(int32_t gdout, int32_t gdin) {   // ezdefset.c:38-170 ; the x
     S.gdin = gdin;
     S.gdout = gdout;
     if (gdin != gdout) {
-        auto &slot = grid_of(gdout)->gsets[gdin];
+        auto &slot = grid_of(gdout)->ds().gsets[gdin];
         if (!slot) {
             slot = std::make_unique<Gset>();
             slot->gdin = gdin;

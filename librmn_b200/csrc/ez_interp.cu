@@ -774,7 +774,10 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         InterpArgs ar = a;
         ar.tile_cap_rs = rs_cap(rs_p, a.tile_cap_rs);   // a.tile_cap_rs arrives as the tallest box height
         const size_t smem_rs = (size_t)RS_NSTAGE * LPS * ar.tile_cap_rs * sizeof(float) + 2 * (size_t)TO * RS_VP * sizeof(float4) + TO * sizeof(double);
-        static bool attr_set = false;
+        static bool attr_set_dev[64] = {false};   // cudaFuncSetAttribute applies to the current device only
+        int cur_dev = 0;
+        cudaGetDevice(&cur_dev);
+        bool &attr_set = attr_set_dev[cur_dev & 63];
         if (!attr_set) {
             const int mx = 227 * 1024;
             cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
