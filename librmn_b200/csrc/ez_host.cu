@@ -197,7 +197,7 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     int last_tiles[3] = {0, 0, 0};   // tiles on the row-separable kernel, on the window kernel, active tiles
     int last_path = 0;          // kernels used by the last interpolation launch: 1 per-point, 2 window tile kernel, 4 per-point on the compacted list, 8 row-separable tile kernel
     int last_nlist = 0;
-    DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4];
+    DevBuf st_in[2], st_out[2], st_fs, st_scratch, st_misc[4], st_xpn;
     // host-pointer pipeline (ezsint_pipelined): two copy streams beside the compute stream, double-buffered chunks
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -1013,6 +1013,22 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     a.npts = out.ni * out.nj;
     a.o = snapshot_opts(vector, sym_sign);
     a.polerow = polerow;
+    if (!gs->yy && (in.needs_expansion || in.axe_y_inverse)) {
+        // ezsint.c:100-113: hemispheric sources are mirrored about the equator (with the sign of the field's symmetry) and
+        // y-inverted ones flipped, once per call, into the logical layout z(ni, j1:j2); every kernel downstream -- the tile
+        // kernels included -- then sees a plain field (xpn / yinv cleared in the descriptor it is given)
+        const long exp_stride = (long)in.ni * (in.j2 - in.j1 + 1);
+        float *d_exp = (float *)S.st_xpn.get((size_t)exp_stride * nfields * sizeof(float));
+        if (!d_exp) { fprintf(stderr, "<ezb200> cannot allocate the expanded source field\n"); return -1; }
+        ezk::expand_field(a.src, d_zin, d_exp, in_stride, exp_stride, nfields, sym_sign, S.stream);
+        S.launches++;
+        a.src.xpn = XPN_NONE;
+        a.src.yinv = 0;
+        a.zin = d_exp;
+        a.in_stride = exp_stride;
+        d_zin = d_exp;
+        in_stride = exp_stride;
+    }
     int rc = 0;
     if (gs->yy) {
         Grid *yin = grid_of(in.subgrid[0]), *yan = grid_of(in.subgrid[1]);
@@ -1050,7 +1066,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     a.out_ni = out.ni;
     a.out_nj = out.nj;
     // (fields of one call may come from different allocations -- the fused (u, v) launch --, so the first and the last are checked)
-    const size_t field_bytes = (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)in.ni * in.nj) * sizeof(float);
+    const size_t field_bytes = (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)a.src.ni * (a.src.j2 - a.src.j1 + 1)) * sizeof(float);
     // Few fields: a tile CTA's set-up (descriptor, copies in flight, plans) is not amortised and the per-point kernel wins
     // (measured: C1 bilinear 1 field, C3 cubic 2 fields; profiles/r2_single_call.md).  EZB200_TILED_MIN_FIELDS overrides.
     static const int tiled_min_fields = getenv("EZB200_TILED_MIN_FIELDS") ? atoi(getenv("EZB200_TILED_MIN_FIELDS")) : 1;

@@ -647,6 +647,20 @@ __global__ void __launch_bounds__(TPB) k_mask(const float *__restrict__ x, const
     mask_out[k] = m;
 }
 
+// ez_xpnsrcgd (ez_xpngdag2 / ez_xpngdb2) + permut, ezsint.c:100-113: the logical field z(ni, j1:j2) of a hemispheric and / or
+// y-inverted source, materialised once per call so that every kernel downstream (tile kernels included) sees a plain field
+__global__ void __launch_bounds__(TPB) k_expand_field(GridDev g, const float *__restrict__ zin, float *__restrict__ zexp, long in_stride, long exp_stride,
+                                                      int sym_sign) {
+    const int f = blockIdx.y;
+    FieldFetch ff = make_fetch(g, zin + (long)f * in_stride, sym_sign);
+    float *o = zexp + (long)f * exp_stride;
+    const long total = (long)g.ni * (g.j2 - g.j1 + 1);
+    for (long k = (long)blockIdx.x * TPB + threadIdx.x; k < total; k += (long)gridDim.x * TPB) {
+        const int i = (int)(k % g.ni) + 1, j = (int)(k / g.ni) + g.j1;
+        o[k] = ff(i, j);
+    }
+}
+
 // ez_corrbgd.inc:29-52: one thread per (field, pole row), sequential fp32 sum
 __global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -683,6 +697,15 @@ __global__ void k_cell_keys(const float *__restrict__ x, const float *__restrict
 #include "ez_interp_rowsep.cuh"
 
 namespace ezk {
+
+void expand_field(const GridDev &g, const float *zin, float *zexp, long in_stride, long exp_stride, int nfields, int sym_sign, cudaStream_t s) {
+    if (nfields <= 0) return;
+    const long total = (long)g.ni * (g.j2 - g.j1 + 1);
+    int bx = (int)((total + (long)TPB * 4 - 1) / ((long)TPB * 4));
+    if (bx < 1) bx = 1;
+    if (bx > 1184) bx = 1184;
+    k_expand_field<<<dim3(bx, nfields), TPB, 0, s>>>(g, zin, zexp, in_stride, exp_stride, sym_sign);
+}
 
 void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s) {
     if (a.nfields <= 0) return;

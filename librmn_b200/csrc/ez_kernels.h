@@ -85,6 +85,8 @@ void ll2xy_u(const GridDev &yin, const GridDev &yan, const int myin[4], const in
              int npts, cudaStream_t s);
 void split_u(const float *y, int njyin, float *ty, uint8_t *zb, int npts, cudaStream_t s);
 
+// K11 hemispheric mirror expansion / y inversion of a source field into its logical layout z(ni, j1:j2) (ez_xpnsrcgd, permut)
+void expand_field(const GridDev &g, const float *zin, float *zexp, long in_stride, long exp_stride, int nfields, int sym_sign, cudaStream_t s);
 // K10 pre-pass: per-field pole-row means (sequential fp32 sums, bit-faithful to ez_calcpoleval) and min/max.
 void field_scalars(const InterpArgs &a, int need_poles, int need_minmax, FieldScalars *fs, unsigned int *scratch, cudaStream_t s);
 // K0-K9: the gather-interpolation kernel.  Returns the number of kernel launches issued.

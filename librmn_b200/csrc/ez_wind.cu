@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(256) k_polar_wind(PolarWindArgs a) {
     }
     if (g.yinv) jj = g.nj + 1 - jj;
     const int row = 1;   // (only the longitude of the column enters below)
-    const float *u = a.u + (long)f * a.stride + (long)(jj - 1) * ni;
-    const float *v = a.v + (long)f * a.stride + (long)(jj - 1) * ni;
+    const int srow = (g.xpn == XPN_NONE && !g.yinv) ? jj - g.j1 : jj - 1;   // storage row (plain fields start at logical row j1)
+    const float *u = a.u + (long)f * a.stride + (long)srow * ni;
+    const float *v = a.v + (long)f * a.stride + (long)srow * ni;
     const char t = south ? 'S' : 'N';
     const float dgrw = south ? a.dgrw_s : a.dgrw_n;
     const bool weighted = (g.grtyp == 'Z' && g.grref == 'E');

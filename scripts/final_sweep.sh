@@ -1,19 +1,21 @@
 # Round-end measurement sweep (run under gpurun): bench lines for every workload + reference arm, launch list, ncu per tile kernel.
 # usage: bash scripts/final_sweep.sh <tag>
-T=${1:-r1x}
-python bench.py 2>/dev/null | tail -1 > gpurun_out/${T}_bench_c2.json
-python bench.py --workload c5 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/${T}_bench_c5.json
-python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${T}_bench_ref.json
-for w in c1 c3 c4; do python bench.py --no-cpu-baseline --workload $w --steps 10 2>/dev/null | tail -1 > gpurun_out/${T}_bench_$w.json; done
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches_c2_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_interp_(tiled|rowsep)" -s 4 -c 2 -f -o gpurun_out/${T}_c2_tilekernels python scripts/prof_run.py c2 2 80 4 2>&1 | tail -1
-ncu --set full --clock-control none --import-source on -k regex:rowsep -s 2 -c 1 -f -o gpurun_out/${T}_c5_rowsep python scripts/prof_run.py c5 2 80 4 2>&1 | tail -1
+T=${1:-r2x}
+timeout 300 python bench.py 2>gpurun_out/${T}_bench_c2.err | tail -1 > gpurun_out/${T}_bench_c2.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${T}_bench_ref.json
+for w in c1 c3 c4 c5; do timeout 200 python bench.py --no-cpu-baseline --workload $w --steps 20 2>/dev/null | tail -1 > gpurun_out/${T}_bench_$w.json; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches_c2_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_interp_(tiled|rowsep)" -s 4 -c 2 -f -o gpurun_out/${T}_c2_tilekernels python scripts/prof_run.py c2 2 80 4 2>&1 | tail -1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:rowsep -s 2 -c 1 -f -o gpurun_out/${T}_c5_rowsep python scripts/prof_run.py c5 2 80 4 2>&1 | tail -1
+timeout 300 compute-sanitizer --tool memcheck python scripts/sanitize_small.py > gpurun_out/${T}_sanitizer_memcheck.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_memcheck.txt
+timeout 300 compute-sanitizer --tool racecheck python scripts/sanitize_small.py > gpurun_out/${T}_sanitizer_racecheck.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_racecheck.txt
 python - <<PY
 import json
 for w in ("c2","c5","c1","c3","c4"):
-    d=json.load(open("gpurun_out/${T}_bench_%s.json"%w))
-    r=d["roofline"]
-    print(w, "%.3f ms"%d["ms_per_step"], "%.3e pts/s"%d["value"], "e2e %.3e"%d["e2e"]["value"], r["kernel"], "frac %.3f"%r["frac"], "step frac %.3f"%r.get("step",{}).get("frac",r["frac"]), "build %.0f ms"%d["gridset_build_ms"])
+    try:
+        d=json.load(open("gpurun_out/${T}_bench_%s.json"%w))
+        r=d["roofline"]
+        print(w, "%.4f ms"%d["ms_per_step"], "%.3e pts/s"%d["value"], "e2e %.3e"%d["e2e"]["value"], r["kernel"], "frac %.3f"%r["frac"], "step frac %.3f"%r.get("step",{}).get("frac",r["frac"]), "build %.0f ms"%d["gridset_build_ms"])
+    except Exception as e: print(w, "ERR", e)
 d=json.load(open("gpurun_out/${T}_bench_ref.json")); print("ref", d["value"], d["cpu_baseline"]["sample"])
-d=json.load(open("gpurun_out/${T}_bench_c2.json")); print(d["roofline"]["kernels"]); print(d["cpu_baseline"])
 PY
