@@ -140,7 +140,7 @@ int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, ui
 int64_t c_ezb200_launch_count(int32_t reset);
 /* kernels used by the calling thread's last interpolation launch: bit 0 per-point kernel, bit 1 window tile kernel,
    bit 2 per-point kernel on the compacted list of points the tiles leave out (*nlist = its length),
-   bit 3 row-separable tile kernel */
+   bit 3 row-separable tile kernel, bit 4 direct kernel (calls of a few fields, c_ezb200_set_direct_max_fields) */
 int32_t c_ezb200_last_path(int32_t *nlist);
 /* block until the calling thread's stream is idle ; returns 0 or -1 with the CUDA error on stderr */
 /* Measurement aid: with timing on, every tiled interpolation launch records CUDA events on the session stream around its
@@ -162,6 +162,12 @@ int32_t c_ezb200_set_rows(int32_t j0, int32_t j1);
  * Returns the number of devices that will be used (clamped to the visible ones); 1 = single device (default).
  * The environment variable EZB200_DEVICES sets the initial value for every thread. */
 int32_t c_ezb200_set_devices(int32_t n);
+/* Kernel choice by field count: a call of at most n fields (c_ezsint = 1, c_ezuvint = 2 per pair, *_batch = their count) runs on
+ * the direct kernel (one thread per target point, no per-tile set-up; for one (u, v) pair the grid-to-grid wind rotation is
+ * applied before the store); larger calls run on the tile kernels, whose set-up is amortised over the levels.  Both evaluate the
+ * same fp32 difference form from the same plans and agree within rounding of the field's local variation (~1e-7 of its range).
+ * Default 4 (environment: EZB200_DIRECT_MAX_FIELDS); 0 = tile kernels for every call.  Per calling thread; returns the previous value. */
+int32_t c_ezb200_set_direct_max_fields(int32_t n);
 int32_t c_ezb200_sync(void);
 const char *c_ezb200_version(void);
 

@@ -102,6 +102,7 @@ class EzLib:
             L.c_ezb200_set_timing.argtypes = [_i32]
             L.c_ezb200_set_rows.argtypes = [_i32, _i32]
             L.c_ezb200_set_devices.argtypes = [_i32]
+            L.c_ezb200_set_direct_max_fields.argtypes = [_i32]
             L.c_ezb200_last_kernel_ms.argtypes = [C.POINTER(C.c_float), C.POINTER(_i32)]
 
     # ---- descriptors -------------------------------------------------------------------------
@@ -268,6 +269,10 @@ class EzLib:
     def set_devices(self, n=1):
         """Fan host-array batch calls of this thread out over n CUDA devices (one gridset replica each); returns the number used."""
         return self.lib.c_ezb200_set_devices(n)
+
+    def set_direct_max_fields(self, n=4):
+        """Calls of at most n fields take the direct kernel, larger ones the tile kernels (0 = always the tile kernels); returns the previous n."""
+        return self.lib.c_ezb200_set_direct_max_fields(n)
 
     def set_rows(self, j0=-1, j1=-1):
         """Output-row band [j0, j1) of the target for this thread's following calls; no arguments = whole target again."""

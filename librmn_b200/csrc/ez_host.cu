@@ -58,6 +58,11 @@ struct TilePlan {   // classification of the target points for the tiled kernel 
     unsigned int *d_rowy = nullptr;   // row-separable tiles: y of each target row (ez_interp_rowsep.cuh)
     int nlist = 0, ntiles_fast = 0, cap = 0;
     int ntiles_rowsep = 0, vw = 0, cap_rs = 0;
+    // constant extrapolation value (extrap_degree = maximum / minimum / value): d_list split into the points outside the source
+    // (plain stores, d_clist) and the rest (d_list2); built on the first launch that wants it
+    int *d_list2 = nullptr, *d_clist = nullptr;
+    int nlist2 = 0, nclist = 0;
+    bool const_tried = false, const_ok = false;
     // plan cache (ez_interp_tiled.cuh: k_plan_cache): stencil origin, fp32 weights and s of every target point
     int *d_pc_idx = nullptr;
     float4 *d_pc_wx = nullptr, *d_pc_wy = nullptr;
@@ -76,6 +81,11 @@ struct Gset {   // _gridset, ez_def.h:148-166, device-resident
     bool wrot_tried = false;
     int *d_perm = nullptr;      // 'Y' cloud targets: the points sorted by source cell (gather locality), built on first use
     bool perm_tried = false;
+    // direct kernel (calls of a few fields): the points with zone bits, compacted; [1] leaves out the points that are outside the
+    // source and nothing else (a constant extrapolation value is stored by the direct kernel itself)
+    int *d_zlist[2] = {nullptr, nullptr};
+    int nzlist[2] = {0, 0};
+    bool zlist_built[2] = {false, false};
     int counts[6] = {0, 0, 0, 0, 0, 0};   // DEHORS, AU_NORD, AU_SUD, POLE_NORD, POLE_SUD, yang
     // 'Y' cloud SOURCE (ez_cloud.cu; the reference's _ygrid, ez_def.h:136-146): k nearest source points and weights per target point
     bool cloud = false;
@@ -186,6 +196,8 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     bool stream_user = false;   // set by the caller: never replaced
     cudaStream_t own_stream = nullptr;   // a private non-blocking stream for host-pointer calls of threads that never set one (HostCallStream)
     int devices = env_devices();   // c_ezb200_set_devices (initial value: EZB200_DEVICES, default 1): GPUs a host-pointer multi-field call of this thread is fanned out over
+    int direct_max = getenv("EZB200_DIRECT_MAX_FIELDS") ? atoi(getenv("EZB200_DIRECT_MAX_FIELDS")) : 4;   // c_ezb200_set_direct_max_fields
+    int call_fields = 0;        // fields of the API call in progress (a call cut into level chunks or device blocks picks its kernels by the whole call's count)
     int row0 = -1, row1 = -1;   // c_ezb200_set_rows: output-row band [row0, row1) of the target (multi-GPU split of one field); -1 = whole target
     int arith = 2;   // 0 reference order, 1 fp64 weight form, 2 fp32 difference form + tiled kernel (default)
     long launches = 0;
@@ -838,7 +850,7 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
     if (tp.suitable && tp.nlist > 0) {
         if (cudaMalloc((void **)&tp.d_list, (size_t)tp.nlist * sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); tp.d_list = nullptr; free_plan(); return nullptr; }
         cudaMemsetAsync(d_counters, 0, sizeof(unsigned int), S.stream);
-        ezk::tile_list(a, tp.d_flags, tp.d_list, d_counters, S.stream);
+        ezk::tile_list(a, tp.d_flags, tp.d_list, d_counters, 0, S.stream);
         S.launches++;
         if (cudaStreamSynchronize(S.stream) != cudaSuccess) {   // the plan is shared by every session: complete before it is published
             fprintf(stderr, "<ezb200> tile list build failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -855,6 +867,36 @@ TilePlan *ensure_tileplan(Gset &gs, const InterpArgs &a) {
                 hc[7] / (8.0 * (tp.ntiles_fast - tp.ntiles_rowsep > 0 ? tp.ntiles_fast - tp.ntiles_rowsep : 1)), tp.cap);
     tp.built = true;
     return &tp;
+}
+
+// The per-point list of a tile plan without its constant-extrapolation points, and those points (see TilePlan).
+void ensure_const_split(TilePlan &tp, const InterpArgs &a) {
+    if (tp.const_tried) return;
+    tp.const_tried = true;
+    if (!tp.suitable || tp.nlist <= 0) return;
+    unsigned int *d_counters = (unsigned int *)S.st_misc[3].get(8 * sizeof(unsigned int));
+    if (!d_counters) return;
+    if (cudaMalloc((void **)&tp.d_list2, (size_t)tp.nlist * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&tp.d_clist, (size_t)tp.nlist * sizeof(int)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(tp.d_list2); cudaFree(tp.d_clist);
+        tp.d_list2 = tp.d_clist = nullptr;
+        return;
+    }
+    unsigned int n[2] = {0, 0};
+    cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), S.stream);
+    ezk::tile_list(a, tp.d_flags, tp.d_list2, d_counters, 1, S.stream);
+    ezk::tile_list(a, tp.d_flags, tp.d_clist, d_counters + 1, 2, S.stream);
+    S.launches += 2;
+    if (cudaMemcpyAsync(n, d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+        cudaStreamSynchronize(S.stream) != cudaSuccess || (long)n[0] + (long)n[1] != (long)tp.nlist) {
+        (void)cudaGetLastError();
+        cudaFree(tp.d_list2); cudaFree(tp.d_clist);
+        tp.d_list2 = tp.d_clist = nullptr;
+        return;
+    }
+    tp.nlist2 = (int)n[0];
+    tp.nclist = (int)n[1];
+    tp.const_ok = true;
 }
 
 // Plan cache of a tile plan, built on the first launch that wants it (see sint_dev): 40 B per target point.
@@ -882,6 +924,8 @@ void free_gset(Gset &gs) {
         if (tp.d_tiles) cudaFree(tp.d_tiles);
         if (tp.d_flags) cudaFree(tp.d_flags);
         if (tp.d_list) cudaFree(tp.d_list);
+        if (tp.d_list2) cudaFree(tp.d_list2);
+        if (tp.d_clist) cudaFree(tp.d_clist);
         if (tp.d_wintiles) cudaFree(tp.d_wintiles);
         if (tp.d_rowy) cudaFree(tp.d_rowy);
         if (tp.d_pc_idx) cudaFree(tp.d_pc_idx);
@@ -894,6 +938,8 @@ void free_gset(Gset &gs) {
     if (gs.d_y) cudaFree(gs.d_y);
     if (gs.d_zb) cudaFree(gs.d_zb);
     if (gs.d_perm) cudaFree(gs.d_perm);
+    for (int k = 0; k < 2; k++)
+        if (gs.d_zlist[k]) cudaFree(gs.d_zlist[k]);
     if (gs.d_wrot) cudaFree(gs.d_wrot);
     if (gs.d_cidx) cudaFree(gs.d_cidx);
     if (gs.d_cwts) cudaFree(gs.d_cwts);
@@ -901,6 +947,7 @@ void free_gset(Gset &gs) {
     gs.d_cidx = gs.d_cmask = nullptr; gs.d_cwts = nullptr; gs.cloud = false;
     gs.d_wrot = nullptr; gs.wrot_tried = false;
     gs.d_perm = nullptr; gs.perm_tried = false;
+    for (int k = 0; k < 2; k++) { gs.d_zlist[k] = nullptr; gs.nzlist[k] = 0; gs.zlist_built[k] = false; }
     gs.d_x = gs.d_y = nullptr;
     gs.d_zb = nullptr;
     gs.built = false;
@@ -980,8 +1027,53 @@ size_t out_points(const Grid &out) {
 }
 
 // zin/zout are DEVICE pointers here.  Returns 0, 2 (extrapolated) or -1.
+// fork / join resources of the session: kernels of one launch that write disjoint target points run on separate streams
+bool ensure_fork() {
+    if (!S.fork_tried) {
+        S.fork_tried = true;
+        static const bool conc_on = !(getenv("EZB200_CONCURRENT") && atoi(getenv("EZB200_CONCURRENT")) == 0);
+        S.fork_ok = conc_on && cudaStreamCreateWithFlags(&S.fork.aux[0], cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&S.fork.aux[1], cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&S.fork.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&S.fork.ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&S.fork.ev_join[1], cudaEventDisableTiming) == cudaSuccess;
+        if (!S.fork_ok) (void)cudaGetLastError();
+    }
+    return S.fork_ok;
+}
+
+// Zone list of a gridset for the direct kernel, built on first use (shared by every session: complete before it is published).
+bool ensure_zonelist(Gset &gs, int skip_dehors_only, int npts) {
+    const int k = skip_dehors_only ? 1 : 0;
+    if (gs.zlist_built[k]) return true;
+    const int *c = gs.counts;
+    const long bound = std::min<long>(npts, (long)(skip_dehors_only ? 0 : c[0]) + c[1] + c[2] + c[3] + c[4]);
+    gs.nzlist[k] = 0;
+    if (bound > 0) {
+        unsigned int *d_cursor = (unsigned int *)S.st_misc[3].get(8 * sizeof(unsigned int));
+        if (!d_cursor) return false;
+        if (cudaMalloc((void **)&gs.d_zlist[k], (size_t)bound * sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); gs.d_zlist[k] = nullptr; return false; }
+        unsigned int n = 0;
+        cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), S.stream);
+        ezk::zone_list(gs.d_zb, npts, skip_dehors_only, gs.d_zlist[k], d_cursor, S.stream);
+        S.launches++;
+        if (cudaMemcpyAsync(&n, d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
+            cudaStreamSynchronize(S.stream) != cudaSuccess || (long)n > bound) {
+            fprintf(stderr, "<ezb200> zone list build failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(gs.d_zlist[k]);
+            gs.d_zlist[k] = nullptr;
+            return false;
+        }
+        gs.nzlist[k] = (int)n;
+    }
+    gs.zlist_built[k] = true;
+    return true;
+}
+
+// wrot / fused: c_ezuvint of one pair hands in the cached wind rotation; *fused reports whether the launch applied it
 int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign,
-             const float *polerow = nullptr) {
+             const float *polerow = nullptr, const float4 *wrot = nullptr, bool *fused = nullptr) {
+    if (fused) *fused = false;
     if (check_degree() < 0) return -1;
     Gset *gs = ensure_gset(out, in);
     if (!gs) return -1;
@@ -1030,6 +1122,8 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
         in_stride = exp_stride;
     }
     int rc = 0;
+    ezk::DirectPre pre;   // per-field scalars pre-pass (pole means, extrapolation value), launched once the kernel path is known
+    memset(&pre, 0, sizeof(pre));
     if (gs->yy) {
         Grid *yin = grid_of(in.subgrid[0]), *yan = grid_of(in.subgrid[1]);
         a.src = to_dev(*yin);
@@ -1056,19 +1150,66 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             FieldScalars *fs = (FieldScalars *)S.st_fs.get((size_t)nfields * sizeof(FieldScalars));
             unsigned int *scr = (unsigned int *)S.st_scratch.get((size_t)nfields * 2 * sizeof(unsigned int));
             if (!fs || !scr) return -1;
-            int need_poles = (!vector) && (c[1] + c[2] + c[3] + c[4] > 0);
-            int need_minmax = (!vector) && c[0] > 0 && (S.opt.degre_extrap == EZ_MAXIMUM || S.opt.degre_extrap == EZ_MINIMUM);
-            ezk::field_scalars(a, need_poles, need_minmax, fs, scr, S.stream);
-            S.launches += need_minmax ? 3 : 1;
-            a.fs = fs;
+            // (vector components never read them: their pole values come from the synthetic pole rows, their outside value is 0)
+            pre.run = !vector;
+            pre.need_poles = (!vector) && (c[1] + c[2] + c[3] + c[4] > 0);
+            pre.need_minmax = (!vector) && c[0] > 0 && (S.opt.degre_extrap == EZ_MAXIMUM || S.opt.degre_extrap == EZ_MINIMUM);
+            pre.fs = fs; pre.scratch = scr;
+            a.fs = vector ? nullptr : fs;
         }
     }
     a.out_ni = out.ni;
     a.out_nj = out.nj;
     // (fields of one call may come from different allocations -- the fused (u, v) launch --, so the first and the last are checked)
     const size_t field_bytes = (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)a.src.ni * (a.src.j2 - a.src.j1 + 1)) * sizeof(float);
-    // Few fields: a tile CTA's set-up (descriptor, copies in flight, plans) is not amortised and the per-point kernel wins
-    // (measured: C1 bilinear 1 field, C3 cubic 2 fields; profiles/r2_single_call.md).  EZB200_TILED_MIN_FIELDS overrides.
+    // Few fields (c_ezsint of one field, c_ezuvint of one pair): a tile CTA's set-up (descriptor, plans of four points per thread,
+    // a copy pipeline with one stage to fill) is all there is to such a launch; the direct kernel (ez_interp_fast.cuh) takes it.
+    // The choice follows the field count of the API CALL, not of the level chunk or device block at hand, so that a call's
+    // result does not depend on how it was cut.  c_ezb200_set_direct_max_fields / EZB200_DIRECT_MAX_FIELDS override (0 = never).
+    if ((S.call_fields > 0 ? S.call_fields : nfields) <= S.direct_max && nfields <= 8 && ezk::direct_eligible(a) && out.grtyp != 'Y') {
+        const Band band = band_of(out);
+        if (band.on && band.j1 <= band.j0) return rc;
+        int nz = 0;
+        const int *zl = nullptr;
+        if (a.use_zones) {
+            const int k = (a.o.extrap >= EZ_MAXIMUM) ? 1 : 0;
+            if (!ensure_zonelist(*gs, k, a.npts)) return -1;
+            zl = gs->d_zlist[k]; nz = gs->nzlist[k];
+        }
+        float *zo = d_zout;
+        if (band.on) {   // full-grid indexing lands in the band buffer
+            a.band_j0 = band.j0; a.band_j1 = band.j1;
+            zo = d_zout - (long)band.j0 * out.ni;
+            a.zout = zo;
+        }
+        a.wrot = (wrot && nfields == 2) ? wrot : nullptr;
+        S.launches += ezk::interp_direct(a, zl, nz, S.stream, ensure_fork() ? &S.fork : nullptr, &pre);
+        if (a.wrot) {
+            if (nz > 0) {
+                ezk::wind_apply_list(a.wrot, zo, zo + out_stride, 0, 1, zl, nz, band.j0 * out.ni, band.j1 * out.ni, S.stream);
+                S.launches++;
+            }
+            if (fused) *fused = true;
+        }
+        S.last_path = 16 | (nz > 0 ? 4 : 0);
+        S.last_nlist = nz;
+        S.last_tiles[0] = S.last_tiles[1] = S.last_tiles[2] = 0;
+        S.timing_valid = false;
+        if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
+            if (band.on) {
+                fprintf(stderr, "<ezb200> output-row bands are not supported for 'B' targets fed from a rotated source (pole rows are averaged over the whole row set)\n");
+                return -1;
+            }
+            ezk::corrbgd(d_zout, out_stride, nfields, out.ni, out.nj, out.ig[0], S.stream);   // ez_corrval.c:144-147
+            S.launches++;
+        }
+        CUDA_OK(cudaGetLastError());
+        return rc;
+    }
+    if (pre.run) {
+        ezk::field_scalars(a, pre.need_poles, pre.need_minmax, pre.fs, pre.scratch, S.stream);
+        S.launches += pre.need_minmax ? 3 : 1;
+    }
     static const int tiled_min_fields = getenv("EZB200_TILED_MIN_FIELDS") ? atoi(getenv("EZB200_TILED_MIN_FIELDS")) : 1;
     if (nfields >= tiled_min_fields && ezk::tiled_eligible(a) && source_blocks_inside_allocation(d_zin, field_bytes) &&
         (nfields == 1 || source_blocks_inside_allocation(d_zin + (long)(nfields - 1) * in_stride, field_bytes))) {
@@ -1094,6 +1235,10 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.win_tiles = tp->d_wintiles;
             a.list = tp->d_list;
             a.nlist = tp->nlist;
+            if (a.use_zones && a.o.extrap >= EZ_MAXIMUM && gs->counts[0] > 0 && tp->nlist > 0) {
+                ensure_const_split(*tp, a);
+                if (tp->const_ok) { a.list = tp->d_list2; a.nlist = tp->nlist2; a.clist = tp->d_clist; a.nclist = tp->nclist; }
+            }
         }
     }
     // scattered ('Y' cloud) targets arrive in arbitrary order: the per-point kernel walks them sorted by source cell
@@ -1124,7 +1269,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.zout = d_zout - off;
         } else {
             // any other band: the per-point kernel on the band's points (same plans, same arithmetic class as a full per-point call)
-            a.tiles = nullptr; a.tile_flags = nullptr; a.list = nullptr; a.nlist = 0;
+            a.tiles = nullptr; a.tile_flags = nullptr; a.list = nullptr; a.nlist = 0; a.clist = nullptr; a.nclist = 0;
             a.ntiles_rowsep = a.ntiles_window = 0;
             a.pc_idx = nullptr; a.pc_wx = a.pc_wy = nullptr; a.pc_sm1 = nullptr;
             a.x += off; a.y += off;
@@ -1133,24 +1278,14 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.out_nj = band.j1 - band.j0;
         }
     }
-    S.last_path = a.tiles ? ((a.ntiles_window > 0 ? 2 : 0) | (a.nlist > 0 ? 4 : 0) | (a.ntiles_rowsep > 0 ? 8 : 0)) : 1;
-    S.last_nlist = a.tiles ? a.nlist : 0;
+    S.last_path = a.tiles ? ((a.ntiles_window > 0 ? 2 : 0) | ((a.nlist > 0 || a.nclist > 0) ? 4 : 0) | (a.ntiles_rowsep > 0 ? 8 : 0)) : 1;
+    S.last_nlist = a.tiles ? a.nlist + a.nclist : 0;
     S.last_tiles[0] = a.tiles ? a.ntiles_rowsep : 0;
     S.last_tiles[1] = a.tiles ? a.ntiles_window : 0;
     S.last_tiles[2] = S.last_tiles[0] + S.last_tiles[1];
     const bool timed = S.timing && a.tiles && S.tev.ev[0];
     S.timing_valid = timed;
-    if (a.tiles && !S.fork_tried) {
-        S.fork_tried = true;
-        static const bool conc_on = !(getenv("EZB200_CONCURRENT") && atoi(getenv("EZB200_CONCURRENT")) == 0);
-        S.fork_ok = conc_on && cudaStreamCreateWithFlags(&S.fork.aux[0], cudaStreamNonBlocking) == cudaSuccess &&
-                    cudaStreamCreateWithFlags(&S.fork.aux[1], cudaStreamNonBlocking) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&S.fork.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&S.fork.ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&S.fork.ev_join[1], cudaEventDisableTiming) == cudaSuccess;
-        if (!S.fork_ok) (void)cudaGetLastError();
-    }
-    S.launches += ezk::interp(a, S.stream, timed ? &S.tev : nullptr, S.fork_ok ? &S.fork : nullptr);
+    S.launches += ezk::interp(a, S.stream, timed ? &S.tev : nullptr, (a.tiles && ensure_fork()) ? &S.fork : nullptr);
     // ez_corrval.c:144-147: B-grid targets fed from a rotated Z/# source get their pole rows averaged
     if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
         if (band.on) {
@@ -1542,11 +1677,18 @@ int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields,
 
 // Returns -2 when the call is not fanned out (the caller then runs the single-device path), else the reference's return code.
 // block(f0, nf) runs fields [f0, f0 + nf) on the CURRENT thread and device.
+// the field count of the outermost API call in progress (see sint_dev: kernel choice) -- nested entries (device blocks) keep it
+struct CallFields {
+    bool owner;
+    explicit CallFields(int n) : owner(S.call_fields == 0) { if (owner) S.call_fields = n; }
+    ~CallFields() { if (owner) S.call_fields = 0; }
+};
+
 int fan_out(int nfields, bool all_host, const std::function<int(int, int)> &block) {
     const int ndev = std::min(S.devices, visible_devices());
     if (ndev <= 1 || !all_host || nfields < 2 * ndev || S.row0 >= 0) return -2;
     // this thread's session, as the workers must see it
-    const int gdin = S.gdin, gdout = S.gdout, arith = S.arith;
+    const int gdin = S.gdin, gdout = S.gdout, arith = S.arith, call_fields = S.call_fields, direct_max = S.direct_max;
     const Options opt = S.opt;
     const int dev0 = t_dev;
     std::vector<int> devs;
@@ -1564,7 +1706,10 @@ int fan_out(int nfields, bool all_host, const std::function<int(int, int)> &bloc
         const int lo = span[k].first, nf = span[k].second;
         g_workers.submit(devs[k], [=, &block]() -> int {
             S.gdin = gdin; S.gdout = gdout; S.arith = arith; S.opt = opt; S.devices = 1; S.row0 = S.row1 = -1;
-            return block(lo, nf);
+            S.call_fields = call_fields; S.direct_max = direct_max;
+            const int r = block(lo, nf);
+            S.call_fields = 0;
+            return r;
         });
     }
     const int saved = S.devices;
@@ -1583,6 +1728,7 @@ int ezsint_n(float *zout, float *zin, int nfields) {
     Lock lk;
     if (!session_ok("c_ezsint")) return -1;
     if (nfields < 1) return -1;
+    CallFields cf(nfields);
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
     const size_t nin = (size_t)in.ni * in.nj, nout = out_points(out);
     if (S.gdin == S.gdout) {   // ezsint.c:56-60
@@ -1616,9 +1762,9 @@ int ezsint_n(float *zout, float *zin, int nfields) {
 // ---------------------------------------------------------------------------------------------------
 // the vector path: c_ezuvint_orig (ezuvint.c:51-94) / c_ezyyuvint (ezyyuvint.c:28-319)
 // ---------------------------------------------------------------------------------------------------
-int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stride, int mode) {
+// everything of a wind-rotation launch but the fields: frames, target lat/lon, panel bits (band-shifted when a row band is set)
+int wind_args(Grid &out, Grid &in, WindArgs &w, long &boff) {
     if (ensure_latlon(out) < 0) return -1;
-    WindArgs w;
     memset(&w, 0, sizeof(w));
     if (in.nsubgrids > 0) {
         Gset *gs = ensure_gset(out, in);
@@ -1632,32 +1778,48 @@ int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stri
     }
     w.dst = to_dev(out);
     const Band band = band_of(out);
-    const long boff = band.on ? (long)band.j0 * out.ni : 0;   // output-row band: the per-point arrays of the target start at its first row
+    boff = band.on ? (long)band.j0 * out.ni : 0;   // output-row band: the per-point arrays of the target start at its first row
     w.lat = out.ds().d_lat + boff; w.lon = out.ds().d_lon + boff;
     if (w.zb) w.zb += boff;
+    w.npts = out.ni * (band.j1 - band.j0);
+    return 0;
+}
+
+// Cached per-point rotation of the (u,v) -> (u,v) conversion between the frames of `in` and `out` (ez_wind.cu), whole target,
+// built on first use; nullptr when it does not apply (arith 0 keeps the reference's per-call evaluation) or cannot be built.
+const float4 *wind_rotation(Grid &out, Grid &in, const WindArgs &w, long boff) {
+    if (S.arith < 1 || in.id == out.id) return nullptr;
+    Gset *gs = ensure_gset(out, in);
+    if (!gs) return nullptr;
+    if (!gs->wrot_tried) {
+        gs->wrot_tried = true;
+        WindArgs wf = w;   // the cached rotation always covers the whole target
+        wf.lat = out.ds().d_lat; wf.lon = out.ds().d_lon;
+        if (wf.zb) wf.zb -= boff;
+        wf.npts = out.ni * out.nj;
+        if (cudaMalloc((void **)&gs->d_wrot, (size_t)wf.npts * sizeof(float4)) == cudaSuccess) {
+            if (!ezk::wind_matrix(wf, gs->d_wrot, S.stream)) { cudaFree(gs->d_wrot); gs->d_wrot = nullptr; }
+            S.launches += 3;
+        } else {
+            gs->d_wrot = nullptr;
+            (void)cudaGetLastError();
+        }
+    }
+    return gs->d_wrot;
+}
+
+int wind_dev(Grid &out, Grid &in, float *d_u, float *d_v, int nfields, long stride, int mode) {
+    WindArgs w;
+    long boff = 0;
+    if (wind_args(out, in, w, boff) < 0) return -1;
     w.u = d_u; w.v = d_v;
     w.stride = stride;
     w.nfields = nfields;
-    w.npts = out.ni * (band.j1 - band.j0);
     w.mode = mode;
-    if (mode == 0 && S.arith >= 1 && in.id != out.id) {   // cached rotation (ez_wind.cu); arith 0 keeps the reference's per-call evaluation
-        Gset *gs = ensure_gset(out, in);
-        if (gs && !gs->wrot_tried) {
-            gs->wrot_tried = true;
-            WindArgs wf = w;   // the cached rotation always covers the whole target
-            wf.lat = out.ds().d_lat; wf.lon = out.ds().d_lon;
-            if (wf.zb) wf.zb -= boff;
-            wf.npts = out.ni * out.nj;
-            if (cudaMalloc((void **)&gs->d_wrot, (size_t)wf.npts * sizeof(float4)) == cudaSuccess) {
-                if (!ezk::wind_matrix(wf, gs->d_wrot, S.stream)) { cudaFree(gs->d_wrot); gs->d_wrot = nullptr; }
-                S.launches += 3;
-            } else {
-                gs->d_wrot = nullptr;
-                (void)cudaGetLastError();
-            }
-        }
-        if (gs && gs->d_wrot) {
-            ezk::wind_apply(gs->d_wrot + boff, d_u, d_v, stride, nfields, w.npts, S.stream);
+    if (mode == 0) {
+        const float4 *m = wind_rotation(out, in, w, boff);
+        if (m) {
+            ezk::wind_apply(m + boff, d_u, d_v, stride, nfields, w.npts, S.stream);
             S.launches++;
             CUDA_OK(cudaGetLastError());
             return 0;
@@ -1689,6 +1851,7 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
         }
     }
     int r1, r2;
+    bool wind_done = false;
     if (eff_in->id == out.id) {   // c_ezsint's gdin == gdout copy, then the wind conversions still run
         for (int f = 0; f < nfields; f++) {
             cudaMemcpyAsync(d_uo + f * out_stride, ui + f * in_stride, (size_t)out.ni * out.nj * sizeof(float), cudaMemcpyDeviceToDevice, S.stream);
@@ -1733,14 +1896,22 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
             // one (u, v) pair, no synthetic pole rows, no hemispheric mirror (the only place the two components are treated
             // differently): ONE launch over two "fields" whose stride is the distance between the caller's arrays, so the
             // gridset, the plans and the tile setup are read and built once for both components
-            r1 = r2 = sint_dev(out, *eff_in, d_uo, ui, 2, (long)(vi - ui), (long)(d_vo - d_uo), 1, +1, nullptr);
+            // (and, on the direct kernel, the cached wind rotation applied to the pair before it is stored)
+            const float4 *m = nullptr;
+            if (mode == 0) {
+                WindArgs w;
+                long boff = 0;
+                if (wind_args(out, *eff_in, w, boff) < 0) return -1;
+                m = wind_rotation(out, *eff_in, w, boff);
+            }
+            r1 = r2 = sint_dev(out, *eff_in, d_uo, ui, 2, (long)(vi - ui), (long)(d_vo - d_uo), 1, +1, nullptr, m, &wind_done);
         } else {
             r1 = sint_dev(out, *eff_in, d_uo, ui, nfields, in_stride, out_stride, 1, +1, prow_u);
             r2 = sint_dev(out, *eff_in, d_vo, vi, nfields, in_stride, out_stride, 1, -1, prow_v);
         }
         if (r1 < 0 || r2 < 0) return -1;
     }
-    if (wind_dev(out, *eff_in, d_uo, d_vo, nfields, out_stride, mode) < 0) return -1;
+    if (!wind_done && wind_dev(out, *eff_in, d_uo, d_vo, nfields, out_stride, mode) < 0) return -1;
     return (r1 == 2 || r2 == 2) ? 2 : 0;
 }
 
@@ -1748,6 +1919,7 @@ int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields,
     Lock lk;
     if (!session_ok("c_ezuvint")) return -1;
     if (nfields < 1 || check_degree() < 0) return -1;
+    CallFields cf(2 * nfields);
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
     const size_t nin = (size_t)in.ni * in.nj, nout = out_points(out);
     if (out.nsubgrids > 0 && in.nsubgrids > 0 && S.opt.use_1subgrid == 1) {
@@ -1826,6 +1998,11 @@ int32_t c_ezb200_set_devices(int32_t n) {
     if (n < 1) n = 1;
     S.devices = std::min(n, visible_devices());
     return S.devices;
+}
+int32_t c_ezb200_set_direct_max_fields(int32_t n) {
+    const int prev = S.direct_max;
+    S.direct_max = n < 0 ? 0 : n;
+    return prev;
 }
 int32_t c_ezb200_set_rows(int32_t j0, int32_t j1) {
     if (j0 < 0 || j1 <= j0) { S.row0 = S.row1 = -1; return 0; }

@@ -742,6 +742,8 @@ bool sort_points_by_cell(const float *x, const float *y, const uint8_t *zb, int 
     return ok;
 }
 
+bool direct_eligible(const InterpArgs &a) { return direct_args_ok(a); }
+
 bool tiled_eligible(const InterpArgs &a) {
     if (a.o.arith != 2 || (a.o.degree != EZ_LINEAR && a.o.degree != EZ_CUBIC)) return false;
     if (a.out_ni < 2 || a.out_nj < 2) return false;
@@ -767,11 +769,11 @@ void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsign
     else k_tile_classify<1><<<grid, TT * TT, 0, s>>>(a, tiles, flags, rowy, counters);
 }
 
-void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s) {
+void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, int mode, cudaStream_t s) {
     int ntx, nty;
     tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
     dim3 grid(ntx, nty);
-    k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor);
+    k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor, mode);
 }
 
 void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s) {
@@ -788,7 +790,10 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         tile_dims(a.out_ni, a.out_nj, &ntx, &nty);
         dim3 grid(ntx, nty);
         static const size_t smem_pad = getenv("EZB200_WIN_SMEM_PAD") ? (size_t)atol(getenv("EZB200_WIN_SMEM_PAD")) : 0;   // occupancy experiments
-        const size_t smem = (size_t)NSTAGE * LPS * a.tile_cap * sizeof(float) + smem_pad;
+        const int nstages = (a.nfields + LPS - 1) / LPS;
+        const size_t smem = (size_t)(nstages < NSTAGE ? nstages : NSTAGE) * LPS * a.tile_cap * sizeof(float) + smem_pad;   // slots beyond the last stage are never touched
+        static const bool few_on = !(getenv("EZB200_TILED_FEW") && atoi(getenv("EZB200_TILED_FEW")) == 0);
+        const bool few = few_on && nstages == 1;
         // the window kernel: one CTA per tile of the compacted list
         const int win_ctas = a.ntiles_window;
         const dim3 grid_win(win_ctas > 0 ? win_ctas : 1);
@@ -805,6 +810,8 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
             const int mx = 227 * 1024;
             cudaFuncSetAttribute(k_interp_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             cudaFuncSetAttribute(k_interp_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(k_interp_tiled_few<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(k_interp_tiled_few<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             const int mxr = RS_NSTAGE * LPS * (TILE_CAP + 16) * (int)sizeof(float) + 2 * TO * RS_VP * (int)sizeof(float4) + TO * (int)sizeof(double);
 #define EZ_RS_ATTR(P)                                                                                       \
     cudaFuncSetAttribute(k_interp_rowsep<3, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxr); \
@@ -815,17 +822,20 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         }
         // Concurrent mode (no per-kernel timing): the window kernel, the row-separable kernel and the list kernel write
         // disjoint target points; with two or more of them they go to separate streams between a fork and a join event.
-        const int nk = (a.ntiles_rowsep > 0) + (a.ntiles_window > 0) + (a.nlist > 0);
+        const int nk = (a.ntiles_rowsep > 0) + (a.ntiles_window > 0) + (a.nlist > 0 || a.nclist > 0);
         const bool conc = fork && !timing && nk >= 2;
         cudaStream_t s_rs = s, s_list = s;
         if (conc) {
             cudaEventRecord(fork->ev_fork, s);
             if (a.ntiles_window > 0 && a.ntiles_rowsep > 0) { s_rs = fork->aux[0]; cudaStreamWaitEvent(s_rs, fork->ev_fork, 0); }
-            if (a.nlist > 0) { s_list = fork->aux[1]; cudaStreamWaitEvent(s_list, fork->ev_fork, 0); }
+            if (a.nlist > 0 || a.nclist > 0) { s_list = fork->aux[1]; cudaStreamWaitEvent(s_list, fork->ev_fork, 0); }
         }
         if (timing) cudaEventRecord(timing->ev[0], s);
         if (a.ntiles_window > 0 && conc) {   // the largest kernel first
-            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
+            if (few) {
+                if (a.o.degree == EZ_CUBIC) k_interp_tiled_few<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
+                else k_interp_tiled_few<1><<<grid_win, NTHR_WIN, smem, s>>>(a);
+            } else if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
             else k_interp_tiled<1><<<grid_win, NTHR_WIN, smem, s>>>(a);
             launches++;
         }
@@ -842,11 +852,18 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
         }
         if (timing) cudaEventRecord(timing->ev[1], s);
         if (a.ntiles_window > 0 && !conc) {
-            if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
+            if (few) {
+                if (a.o.degree == EZ_CUBIC) k_interp_tiled_few<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
+                else k_interp_tiled_few<1><<<grid_win, NTHR_WIN, smem, s>>>(a);
+            } else if (a.o.degree == EZ_CUBIC) k_interp_tiled<3><<<grid_win, NTHR_WIN, smem, s>>>(a);
             else k_interp_tiled<1><<<grid_win, NTHR_WIN, smem, s>>>(a);
             launches++;
         }
         if (timing) cudaEventRecord(timing->ev[2], s);
+        if (a.nclist > 0) {
+            k_store_const<<<(a.nclist + 255) / 256, 256, 0, s_list>>>(a, a.clist, a.nclist);
+            launches++;
+        }
         if (a.nlist > 0) {
             InterpArgs b = a;
             b.tiles = nullptr;
@@ -865,6 +882,50 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
     int nb = (a.npts + TPB - 1) / TPB;
     k_interp_ref<<<nb, TPB, 0, s>>>(a);
     return 1;
+}
+
+int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork, const DirectPre *pre) {
+    if (a.npts <= 0 || a.nfields <= 0) return 0;
+    const int npts = a.band_j1 > 0 ? (a.band_j1 - a.band_j0) * a.out_ni : a.npts;
+    int launches = 0;
+    // The per-field scalars (pole means, extrapolation value) and the zone points that read them are small, latency-bound
+    // launches: with fork resources they run beside the direct kernel (disjoint target points) instead of around it.  A
+    // constant extrapolation value is read by the direct kernel itself: then the scalars stay in front of it.
+    const bool direct_reads_fs = a.fs && !a.o.vector && a.o.extrap >= EZ_MAXIMUM;
+    const bool conc = fork && nzlist > 0 && !direct_reads_fs;
+    cudaStream_t s_list = s;
+    if (conc) {
+        cudaEventRecord(fork->ev_fork, s);
+        s_list = fork->aux[1];
+        cudaStreamWaitEvent(s_list, fork->ev_fork, 0);
+    }
+    if (pre && pre->run) {
+        field_scalars(a, pre->need_poles, pre->need_minmax, pre->fs, pre->scratch, conc ? s_list : s);
+        launches += pre->need_minmax ? 3 : 1;
+    }
+    if (a.o.degree == EZ_CUBIC) {
+        constexpr int per = TPB * DirectCfg<3>::PPT;
+        k_interp_direct<3><<<(npts + per - 1) / per, TPB, 0, s>>>(a);
+    } else {
+        constexpr int per = TPB * DirectCfg<1>::PPT;
+        k_interp_direct<1><<<(npts + per - 1) / per, TPB, 0, s>>>(a);
+    }
+    launches++;
+    if (nzlist > 0) {
+        InterpArgs b = a;
+        b.list = zlist;
+        b.nlist = nzlist;
+        b.wrot = nullptr;
+        launch_fast(b, s_list);
+        launches++;
+    }
+    if (conc) { cudaEventRecord(fork->ev_join[1], s_list); cudaStreamWaitEvent(s, fork->ev_join[1], 0); }
+    return launches;
+}
+
+void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s) {
+    if (npts <= 0) return;
+    k_zone_list<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(zb, npts, skip_dehors_only, list, cursor);
 }
 
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,

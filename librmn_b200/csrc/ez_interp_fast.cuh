@@ -398,6 +398,116 @@ __global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ Int
         point_body<DEG>(a.src, a, a.zin, n, px, py, zbits);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// the direct kernel: calls of a few fields (c_ezsint of one field, c_ezuvint of one pair -- C1, C3)
+// ---------------------------------------------------------------------------------------------------
+// A tile CTA's set-up (descriptor, plans of four points per thread, a copy pipeline with one stage to fill) is amortised over
+// the levels of a launch; with one or two levels it is all there is, at 2 CTAs per SM.  Here: one thread per target point,
+// no shared memory, few registers (high occupancy hides the gather latency; the source of a single-field call is L2-resident
+// after its first touch), the same fp32 difference form as k_interp_fast<4 / 5>.  Zone points are left out: a constant
+// extrapolation value outside the source (ez_corrval.c:56-93) is a plain store, the polar zones go to the per-point kernel
+// on the gridset's zone list.  With `wrot` (c_ezuvint, one pair = two fields) the cached grid-to-grid wind rotation of
+// ez_wind.cu is applied to the pair before it is stored, in k_wind_apply's own operation order.
+template <int DEG>
+__device__ __forceinline__ void direct_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ z, int n, float px, float py) {
+    const long is = a.in_stride, os = a.out_stride;
+    float *zo = a.zout + n;
+    if (DEG == 1) {
+        const PlanLinF p = to_f32(plan_linear(g, px, py));
+        if (a.wrot) {
+            const float u = eval_linear_f32(p, z), v = eval_linear_f32(p, z + is);
+            const float4 r = __ldg(a.wrot + n);
+            zo[0] = fmaf(r.y, v, r.x * u);
+            zo[os] = fmaf(r.w, v, r.z * u);
+            return;
+        }
+        for (int f = 0; f < a.nfields; f++) zo[f * os] = eval_linear_f32(p, z + f * is);
+    } else {
+        const PlanCubF p = to_f32(plan_cubic(g, px, py));
+        if (a.wrot) {
+            const float u = eval_cubic_f32(p, z), v = eval_cubic_f32(p, z + is);
+            const float4 r = __ldg(a.wrot + n);
+            zo[0] = fmaf(r.y, v, r.x * u);
+            zo[os] = fmaf(r.w, v, r.z * u);
+            return;
+        }
+        for (int f = 0; f < a.nfields; f++) zo[f * os] = eval_cubic_f32(p, z + f * is);
+    }
+}
+
+#ifndef EZ_DIRECT_MINB
+#define EZ_DIRECT_MINB 3
+#endif
+#ifndef EZ_DIRECT_MINB_LIN
+#define EZ_DIRECT_MINB_LIN 4
+#endif
+#ifndef EZ_DIRECT_PPT
+#define EZ_DIRECT_PPT 2
+#endif
+#ifndef EZ_DIRECT_PPT_LIN
+#define EZ_DIRECT_PPT_LIN 4
+#endif
+// points per thread: the kernel is bound by the latency of its dependent chain (coordinates -> gathers -> store), so a thread
+// carries several independent points (TPB apart: every access stays coalesced) and issues all their coordinate loads first
+template <int DEG> struct DirectCfg { static constexpr int PPT = (DEG == 1) ? EZ_DIRECT_PPT_LIN : EZ_DIRECT_PPT; };
+
+template <int DEG>
+__global__ void __launch_bounds__(TPB, DEG == 1 ? EZ_DIRECT_MINB_LIN : EZ_DIRECT_MINB) k_interp_direct(const __grid_constant__ InterpArgs a) {
+    constexpr int PPT = DirectCfg<DEG>::PPT;
+    // output-row band: full-grid indexing from the band's first point (zout points band_j0 rows before the band buffer)
+    const int n0 = a.band_j1 > 0 ? a.band_j0 * a.out_ni : 0, n1 = a.band_j1 > 0 ? a.band_j1 * a.out_ni : a.npts;
+    const int nb = n0 + blockIdx.x * (TPB * PPT) + threadIdx.x;
+    float px[PPT], py[PPT];
+    uint8_t bits[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int n = nb + k * TPB;
+        const bool in = n < n1;
+        px[k] = in ? a.x[n] : 1.f;
+        py[k] = in ? a.y[n] : 1.f;
+        bits[k] = (in && a.zb) ? a.zb[n] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int n = nb + k * TPB;
+        if (n >= n1) continue;
+        const uint8_t zbits = a.use_zones ? (uint8_t)(bits[k] & 0x1f) : (uint8_t)0;
+        if (zbits) {
+            if (zbits == ZB_DEHORS && a.o.extrap >= EZ_MAXIMUM) {
+                const long os = a.out_stride;
+                for (int f = 0; f < a.nfields; f++) a.zout[n + f * os] = (a.o.vector || !a.fs) ? 0.0f : a.fs[f].fudge;
+            }
+            continue;   // every other zone point: k_interp_fast on the zone list
+        }
+        if (a.yy && (bits[k] & ZB_YANG))
+            direct_body<DEG>(a.src2, a, a.zin + a.panel_stride, n, px[k], py[k]);
+        else
+            direct_body<DEG>(a.src, a, a.zin, n, px[k], py[k]);
+    }
+}
+
+// the points with zone bits (optionally without those that are outside the source and nothing else), compacted
+__global__ void __launch_bounds__(TPB) k_zone_list(const uint8_t *__restrict__ zb, int npts, int skip_dehors_only, int *__restrict__ list,
+                                                   unsigned int *__restrict__ cursor) {
+    const int n = blockIdx.x * TPB + threadIdx.x;
+    const uint8_t z = (n < npts) ? (uint8_t)(zb[n] & 0x1f) : (uint8_t)0;
+    const bool take = z != 0 && !(skip_dehors_only && z == ZB_DEHORS);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, take);
+    if (!ballot) return;
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) list[base + __popc(ballot & ((1u << lane) - 1u))] = n;
+}
+
+bool direct_args_ok(const InterpArgs &a) {
+    if (a.o.arith != 2 || (a.o.degree != EZ_LINEAR && a.o.degree != EZ_CUBIC)) return false;
+    if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
+    if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
+    return true;
+}
+
 bool launch_fast(const InterpArgs &a, cudaStream_t s) {
     if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
     if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;

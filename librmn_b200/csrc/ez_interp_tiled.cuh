@@ -269,15 +269,23 @@ __global__ void __launch_bounds__(TT * TT) k_tile_classify(const __grid_constant
 }
 
 // second pass: the points the tile kernel leaves out, compacted (warp-aggregated append; order is irrelevant)
+// mode 0: every point the tile kernels leave out ; 1: those, except the points that are outside the source and in no other zone
+// (with a constant extrapolation value they are plain stores: k_store_const on the list mode 2 builds) ; 2: only those points
 __global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ InterpArgs a, const uint32_t *__restrict__ flags,
-                                                       int *__restrict__ list, unsigned int *__restrict__ cursor) {
+                                                       int *__restrict__ list, unsigned int *__restrict__ cursor, int mode) {
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const Quad q = quad_of_thread(blockIdx.x, blockIdx.y);
     const int ni = a.out_ni, nj = a.out_nj;
     const bool fast = (flags[tile * 8 + (threadIdx.x >> 5)] >> (threadIdx.x & 31)) & 1u;
     int k = 0;
+    bool take[4] = {false, false, false, false};
     if (!fast)
-        for (int p = 0; p < 4; p++) k += q.valid(p, ni, nj) ? 1 : 0;
+        for (int p = 0; p < 4; p++) {
+            if (!q.valid(p, ni, nj)) continue;
+            const bool cst = mode != 0 && a.zb && (a.zb[q.index(p, ni)] & 0x1f) == ZB_DEHORS;
+            take[p] = (mode == 0) || (mode == 1 && !cst) || (mode == 2 && cst);
+            k += take[p] ? 1 : 0;
+        }
     int incl = k;
     const int lane = threadIdx.x & 31;
     for (int o = 1; o < 32; o <<= 1) {
@@ -291,8 +299,19 @@ __global__ void __launch_bounds__(TT * TT) k_tile_list(const __grid_constant__ I
     if (k > 0) {
         unsigned int at = base + (unsigned int)(incl - k);
         for (int p = 0; p < 4; p++)
-            if (q.valid(p, ni, nj)) list[at++] = q.index(p, ni);
+            if (take[p]) list[at++] = q.index(p, ni);
     }
+}
+
+// ez_corrval.c:56-93 with extrap_degree = maximum / minimum / value: the points outside the source get one value per field
+// (0.0 for vector components, :64-67) -- plain stores on a compacted list
+__global__ void __launch_bounds__(256) k_store_const(const __grid_constant__ InterpArgs a, const int *__restrict__ clist, int nclist) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= nclist) return;
+    const int n = clist[t];
+    if (a.band_j1 > 0 && (n < a.band_j0 * a.out_ni || n >= a.band_j1 * a.out_ni)) return;
+    const long os = a.out_stride;
+    for (int f = 0; f < a.nfields; f++) a.zout[n + f * os] = (a.o.vector || !a.fs) ? 0.0f : a.fs[f].fudge;
 }
 
 // third pass: the plan of every target point, stored for the tile kernels (40 B per point)
@@ -536,7 +555,7 @@ __device__ __forceinline__ void window_tile(const GridDev &g, const InterpArgs &
 // plans of the CTA's next tile prefetched) was measured and lost 5-10 %: the hardware's dynamic CTA scheduling de-phases the
 // two resident CTAs of an SM better than a static tile walk does (profiles/r2_window_kernel_log.md).
 template <int DEG>
-__global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) {
+__device__ __forceinline__ void tiled_cta(const InterpArgs &a) {
     extern __shared__ __align__(16) float smem[];
     const int tile = a.win_tiles[blockIdx.x];
     const int ntx = (a.out_ni + TO - 1) / TO;
@@ -552,5 +571,14 @@ __global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_MINB) k_interp_tiled(const 
     if (td.panel) window_tile<DEG>(a.src2, a, td, q, fast, a.zin + a.panel_stride, a.src2.j2 - a.src2.j1 + 1, smem32);
     else window_tile<DEG>(a.src, a, td, q, fast, a.zin, a.src.j2 - a.src.j1 + 1, smem32);
 }
+template <int DEG>
+__global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_MINB) k_interp_tiled(const __grid_constant__ InterpArgs a) { tiled_cta<DEG>(a); }
+// Launches of one pipeline stage (at most LPS fields): the per-tile latency chain (descriptor, plans, copies, barrier) is all there
+// is, so CTAs in flight matter more than registers: 3 CTAs per SM at 80 registers (spills in the plan set-up), one stage of shared memory.
+#ifndef EZ_TILED_FEW_MINB
+#define EZ_TILED_FEW_MINB 3
+#endif
+template <int DEG>
+__global__ void __launch_bounds__(NTHR_WIN, EZ_TILED_FEW_MINB) k_interp_tiled_few(const __grid_constant__ InterpArgs a) { tiled_cta<DEG>(a); }
 
 }  // namespace

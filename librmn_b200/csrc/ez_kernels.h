@@ -46,6 +46,11 @@ struct InterpArgs {
     // per-point kernel restricted to a compacted list of target points (nullptr = all npts points)
     const int *list;
     int nlist;
+    // tiled path with a constant extrapolation value: the points outside the source (and in no other zone), taken off `list`
+    const int *clist;
+    int nclist;
+    // direct kernel, c_ezuvint of one pair: cached grid-to-grid wind rotation (ez_wind.cu), applied to fields (0, 1) before the store
+    const float4 *wrot;
 };
 
 struct WindArgs {
@@ -101,13 +106,24 @@ struct InterpFork {
     cudaEvent_t ev_fork, ev_join[2];
 };
 int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing = nullptr, const InterpFork *fork = nullptr);
+// calls of a few fields: one thread per target point, zone points on `zlist` (nzlist entries) through the per-point kernel
+bool direct_eligible(const InterpArgs &a);
+// pre: the per-field scalars pre-pass of this launch (field_scalars), issued by interp_direct so that it can run beside the kernel
+struct DirectPre {
+    bool run;
+    int need_poles, need_minmax;
+    FieldScalars *fs;
+    unsigned int *scratch;
+};
+int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork = nullptr, const DirectPre *pre = nullptr);
+void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s);
 // scattered targets: permutation of the target points by source cell, for gather locality in the per-point kernel
 bool sort_points_by_cell(const float *x, const float *y, const uint8_t *zb, int ni, int nj, int npts, int *perm, cudaStream_t s);
 // tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry
 bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
 void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *rowy, unsigned int *counters, cudaStream_t s);
-void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, cudaStream_t s);
+void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, int mode, cudaStream_t s);
 void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s);
 // 'Y' point clouds as a SOURCE (ez_cloud.cu): k nearest source points + inverse-square-distance weights per target point
 // ([nw][ndst] plane-major, 1-based indices, 0 = empty slot), and their application to nfields fields
@@ -123,6 +139,7 @@ void wind(const WindArgs &a, cudaStream_t s);
 // cached per-point rotation of the (u,v) -> (u,v) conversion: build once per gridset, apply per call
 bool wind_matrix(const WindArgs &a, float4 *m, cudaStream_t s);
 void wind_apply(const float4 *m, float *u, float *v, long stride, int nfields, int npts, cudaStream_t s);
+void wind_apply_list(const float4 *m, float *u, float *v, long stride, int nfields, const int *list, int nlist, int n0, int n1, cudaStream_t s);
 // K18 synthetic pole rows for vectors (ez_calcnpolarwind.c / ez_calcspolarwind.c)
 void polar_wind_rows(const PolarWindArgs &a, cudaStream_t s);
 // B-grid pole-row averaging, ez_corrbgd.inc:29-52

@@ -283,6 +283,22 @@ __global__ void __launch_bounds__(TPB) k_wind_apply(const float4 *__restrict__ m
     }
 }
 
+// the same rotation on a compacted list of target points (the zone points of a direct-kernel launch, ez_interp_fast.cuh)
+__global__ void __launch_bounds__(TPB) k_wind_apply_list(const float4 *__restrict__ m, float *__restrict__ u, float *__restrict__ v, long stride,
+                                                         int nfields, const int *__restrict__ list, int nlist, int n0, int n1) {
+    const int t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= nlist) return;
+    const int n = list[t];
+    if (n < n0 || n >= n1) return;   // output-row band
+    const float4 r = m[n];
+    for (int f = 0; f < nfields; f++) {
+        const long k = (long)f * stride + n;
+        const float a = u[k], b = v[k];
+        u[k] = fmaf(r.y, b, r.x * a);
+        v[k] = fmaf(r.w, b, r.z * a);
+    }
+}
+
 namespace ezk {
 bool wind_matrix(const WindArgs &a0, float4 *m, cudaStream_t s) {
     float *tmp = nullptr;
@@ -301,6 +317,10 @@ bool wind_matrix(const WindArgs &a0, float4 *m, cudaStream_t s) {
 void wind_apply(const float4 *m, float *u, float *v, long stride, int nfields, int npts, cudaStream_t s) {
     if (npts <= 0 || nfields <= 0) return;
     k_wind_apply<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(m, u, v, stride, nfields, npts);
+}
+void wind_apply_list(const float4 *m, float *u, float *v, long stride, int nfields, const int *list, int nlist, int n0, int n1, cudaStream_t s) {
+    if (nlist <= 0 || nfields <= 0) return;
+    k_wind_apply_list<<<(nlist + TPB - 1) / TPB, TPB, 0, s>>>(m, u, v, stride, nfields, list, nlist, n0, n1);
 }
 void polar_wind_rows(const PolarWindArgs &a, cudaStream_t s) {
     if (a.nfields <= 0) return;

@@ -49,3 +49,12 @@ def cuda_ok():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return True
+
+
+@pytest.fixture
+def tiles_only(ezb):
+    """Calls of 1-4 fields normally take the direct kernel (c_ezb200_set_direct_max_fields); tests that are about the tile
+    kernels, or that compare calls of different field counts bit for bit, switch it off for their duration."""
+    prev = ezb.set_direct_max_fields(0)
+    yield
+    ezb.set_direct_max_fields(prev)

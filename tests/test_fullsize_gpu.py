@@ -97,5 +97,7 @@ def test_full_size_against_oracle(ezb, ezref, cuda_ok, name, arith):
             name, arith, k, int(bad.sum()), g.size, TOL, d.max())
         worst = max(worst, float(d[~bad].max()))
     print("%s arith=%d path=%d list=%d levels=%s max|gpu-oracle|/range=%.2e" % (name, arith, path, nlist, ks, worst))
-    if arith == 2 and name in ("c1", "c2", "c3", "c5"):
+    if arith == 2 and name in ("c2", "c3", "c5"):
         assert path & 10, "%s did not take a tile kernel at full size (path=%d)" % (name, path)
+    if arith == 2 and name == "c1":   # 3 fields: the direct kernel (tests/test_direct_gpu.py runs it on the tile kernels too)
+        assert path & 16, "c1 did not take the direct kernel (path=%d)" % path

@@ -36,9 +36,19 @@ def _call(lib, c, j0=None, j1=None):
         lib.set_rows()
 
 
+@pytest.mark.parametrize("direct_max", [0, 4])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_tile_row_bands_stitch_to_the_full_call_bit_for_bit(ezb, cuda_ok, world):
+def test_tile_row_bands_stitch_to_the_full_call_bit_for_bit(ezb, cuda_ok, world, direct_max):
+    """direct_max = 0: the tile kernels on whole tile rows ; 4: the direct kernel (one field / one pair per call), which takes any band."""
     ezb.set_arith(2)
+    prev = ezb.set_direct_max_fields(direct_max)
+    try:
+        _stitch(ezb, world, 16 if direct_max else 0)
+    finally:
+        ezb.set_direct_max_fields(prev)
+
+
+def _stitch(ezb, world, want_path):
     for c in _cases(ezb):
         c.defset()
         rc_full, full = _call(ezb, c)
@@ -50,6 +60,7 @@ def test_tile_row_bands_stitch_to_the_full_call_bit_for_bit(ezb, cuda_ok, world)
                 rc, band = _call(ezb, c, j0, j1)
                 assert rc == rc_full or rc >= 0, c.name
                 path, _ = ezb.last_path()
+                assert not want_path or (path & want_path), (c.name, path)
                 parts.append(band)
         stitched = np.concatenate(parts, axis=1)
         assert stitched.shape == full.shape, c.name

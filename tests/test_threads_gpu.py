@@ -86,7 +86,7 @@ def test_thread_options_are_thread_local(ezb, cuda_ok):
     assert np.array_equal(got[1][1], ref_nn) and np.array_equal(got[3][1], ref_nn)
 
 
-def test_pageable_and_pinned_host_arrays_agree(ezb, cuda_ok):
+def test_pageable_and_pinned_host_arrays_agree(ezb, cuda_ok, tiles_only):
     """The pinned ring that carries pageable caller arrays (host_pipeline) must not change a bit."""
     import torch
     c = configs.c2(ezb, 1.5, 1.0, "cubic")
