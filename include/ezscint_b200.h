@@ -140,7 +140,8 @@ int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, ui
 int64_t c_ezb200_launch_count(int32_t reset);
 /* kernels used by the calling thread's last interpolation launch: bit 0 per-point kernel, bit 1 window tile kernel,
    bit 2 per-point kernel on the compacted list of points the tiles leave out (*nlist = its length),
-   bit 3 row-separable tile kernel, bit 4 direct kernel (calls of a few fields, c_ezb200_set_direct_max_fields) */
+   bit 3 row-separable tile kernel, bit 4 direct kernel (calls of a few fields, c_ezb200_set_direct_max_fields),
+   bit 5 averaging kernel (interp_degree = average / sph_average) */
 int32_t c_ezb200_last_path(int32_t *nlist);
 /* block until the calling thread's stream is idle ; returns 0 or -1 with the CUDA error on stderr */
 /* Measurement aid: with timing on, every tiled interpolation launch records CUDA events on the session stream around its

@@ -1002,10 +1002,11 @@ InterpOpts snapshot_opts(int vector, int sym_sign) {
     return o;
 }
 
-int check_degree() {
+int check_degree(bool grid_call = false) {
     int d = S.opt.degre_interp;
     if (d == EZ_NEAREST || d == EZ_LINEAR || d == EZ_CUBIC) return 0;
-    fprintf(stderr, "<ezb200> interp_degree average/sph_average is outside the hot-path scope (SURVEY.md 8f N3)\n");
+    if (grid_call && (d == EZ_AVERAGE || d == EZ_SPH_AVERAGE)) return 0;   // c_ezsint / c_ezuvint: ez_avg / ez_avg_sph (sint_dev)
+    fprintf(stderr, "<ezb200> interp_degree average/sph_average applies to grid-to-grid calls only (ez_avg.inc works on the whole target grid)\n");
     return -1;
 }
 
@@ -1074,7 +1075,7 @@ bool ensure_zonelist(Gset &gs, int skip_dehors_only, int npts) {
 int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields, long in_stride, long out_stride, int vector, int sym_sign,
              const float *polerow = nullptr, const float4 *wrot = nullptr, bool *fused = nullptr) {
     if (fused) *fused = false;
-    if (check_degree() < 0) return -1;
+    if (check_degree(true) < 0) return -1;
     Gset *gs = ensure_gset(out, in);
     if (!gs) return -1;
     if (gs->cloud) {
@@ -1162,6 +1163,52 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     a.out_nj = out.nj;
     // (fields of one call may come from different allocations -- the fused (u, v) launch --, so the first and the last are checked)
     const size_t field_bytes = (gs->yy ? 2 * (size_t)a.panel_stride : (size_t)a.src.ni * (a.src.j2 - a.src.j1 + 1)) * sizeof(float);
+    if (a.o.degree == EZ_AVERAGE || a.o.degree == EZ_SPH_AVERAGE) {
+        // gdinterp.c:32-75,118-131: c_gdcompatible_grids decides on the TARGET type alone ; otherwise the call is a linear one
+        if (!(out.grtyp == 'L' || out.grtyp == 'A' || out.grtyp == 'B' || out.grtyp == 'G')) {
+            fprintf(stderr, "(gdinterp) input and output grids are not compatible for average computation\n");
+            fprintf(stderr, "(gdinterp) interpolaton level set to linear\n");
+            a.o.degree = EZ_LINEAR;
+        } else {
+            if (gs->yy || in.needs_expansion || in.axe_y_inverse) {
+                fprintf(stderr, "<ezb200> interp_degree average / sph_average is not supported for 'U', hemispheric or y-inverted sources\n");
+                return -1;
+            }
+            const Band band = band_of(out);
+            if (band.on && band.j1 <= band.j0) return rc;
+            const int sph = a.o.degree == EZ_SPH_AVERAGE;
+            if (sph && ensure_latlon(out) < 0) return -1;
+            int nz = 0;
+            const int *zl = nullptr;
+            if (a.use_zones) {
+                if (!ensure_zonelist(*gs, 0, a.npts)) return -1;
+                zl = gs->d_zlist[0]; nz = gs->nzlist[0];
+            }
+            if (band.on) {   // full-grid indexing lands in the band buffer
+                a.band_j0 = band.j0; a.band_j1 = band.j1;
+                a.zout = d_zout - (long)band.j0 * out.ni;
+            }
+            if (pre.run) {
+                ezk::field_scalars(a, pre.need_poles, pre.need_minmax, pre.fs, pre.scratch, S.stream);
+                S.launches += pre.need_minmax ? 3 : 1;
+            }
+            S.launches += ezk::interp_avg(a, sph ? out.ds().d_lat : nullptr, sph, zl, nz, S.stream);
+            S.last_path = 32 | (nz > 0 ? 4 : 0);
+            S.last_nlist = nz;
+            S.last_tiles[0] = S.last_tiles[1] = S.last_tiles[2] = 0;
+            S.timing_valid = false;
+            if (S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
+                if (band.on) {
+                    fprintf(stderr, "<ezb200> output-row bands are not supported for 'B' targets fed from a rotated source (pole rows are averaged over the whole row set)\n");
+                    return -1;
+                }
+                ezk::corrbgd(d_zout, out_stride, nfields, out.ni, out.nj, out.ig[0], S.stream);   // ez_corrval.c:144-147
+                S.launches++;
+            }
+            CUDA_OK(cudaGetLastError());
+            return rc;
+        }
+    }
     // Few fields (c_ezsint of one field, c_ezuvint of one pair): a tile CTA's set-up (descriptor, plans of four points per thread,
     // a copy pipeline with one stage to fill) is all there is to such a launch; the direct kernel (ez_interp_fast.cuh) takes it.
     // The choice follows the field count of the API CALL, not of the level chunk or device block at hand, so that a call's
@@ -1918,7 +1965,7 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
 int ezuvint_n(float *uuout, float *vvout, float *uuin, float *vvin, int nfields, int mode) {
     Lock lk;
     if (!session_ok("c_ezuvint")) return -1;
-    if (nfields < 1 || check_degree() < 0) return -1;
+    if (nfields < 1 || check_degree(true) < 0) return -1;
     CallFields cf(2 * nfields);
     Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
     const size_t nin = (size_t)in.ni * in.nj, nout = out_points(out);

@@ -661,6 +661,100 @@ __global__ void __launch_bounds__(TPB) k_expand_field(GridDev g, const float *__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// interp_degree = average / sph_average: ez_avg.inc:55-170, ez_avg_sph.inc:65-230
+// ---------------------------------------------------------------------------------------------------
+// One thread per target point.  The target cell runs half-way to its neighbours in source index space, taken from the FIRST
+// row (x) and the FIRST column (y) of the gridset coordinates (the routines assume axis-aligned grids); the spherical
+// variant widens the x extent by 1 / cos(latitude of the target row).  Default-real arithmetic, sums in the reference's loop
+// order, no contraction (-fmad=false): bit-equal to the Fortran for ez_avg; ez_avg_sph differs by the rounding of the row
+// latitude (computed by ez_calclatlon here, by c_gdllfxy_orig at (1, j) there).  A source index outside what the reference
+// allocates and fills (ez_avg.inc:20-52) is undefined there and reads as 0 here.
+struct AvgSrc {
+    const float *z;
+    int ni, nj, ext;
+    __device__ __forceinline__ float operator()(int ii, int jj) const {
+        if (jj < 1 || jj > nj) return 0.0f;
+        int i;
+        if (ext == 0) {
+            if (ii < 1 || ii > ni) return 0.0f;
+            i = ii;
+        } else if (ext == 1) {
+            if (ii < 2 - ni || ii > 2 * ni - 2) return 0.0f;
+            i = ii >= ni ? ii - ni + 1 : (ii >= 1 ? ii : ii + ni - 1);
+        } else {
+            if (ii < 1 - ni || ii > 2 * ni) return 0.0f;
+            i = ii > ni ? ii - ni : (ii >= 1 ? ii : ii + ni);
+        }
+        return __ldg(z + (long)(jj - 1) * ni + (i - 1));
+    }
+};
+__global__ void __launch_bounds__(TPB) k_avg(const __grid_constant__ InterpArgs a, const float *__restrict__ row_lat, int sph) {
+    const int ni_dst = a.out_ni, nj_dst = a.out_nj;
+    const int n0 = a.band_j1 > 0 ? a.band_j0 * ni_dst : 0, n1 = a.band_j1 > 0 ? a.band_j1 * ni_dst : a.npts;
+    const int n = n0 + blockIdx.x * TPB + threadIdx.x;
+    if (n >= n1) return;
+    const int j = n / ni_dst + 1, i = n - (j - 1) * ni_dst + 1;
+    const int ni_src = a.src.ni, nj_src = a.src.nj;
+    // x = xx(:,1), y = yy(1,:) ; if (x(1) > real(ni_src-1)) x(1) = 1.0      (ez_avg.inc:55-57)
+    auto X = [&](int k) { float v = a.x[k - 1]; if (k == 1 && v > (float)(ni_src - 1)) v = 1.0f; return v; };
+    auto Y = [&](int k) { return a.y[(long)(k - 1) * ni_dst]; };
+    float amp = 1.0f;
+    if (sph) amp = 1.0f / cosf(row_lat[(long)(j - 1) * ni_dst] * 0.017453295199f);
+    float xl, xh, yl, yh;
+    const float xi = X(i), yj = Y(j);
+    if (i == 1) { const float h = 0.5f * (X(2) - xi); xl = sph ? xi - h * amp : xi - h; }
+    else { const float h = 0.5f * (xi - X(i - 1)); xl = sph ? xi - h * amp : xi - h; }
+    if (i == ni_dst) { const float h = 0.5f * (xi - X(i - 1)); xh = sph ? xi + h * amp : xi + h; }
+    else { const float h = 0.5f * (X(i + 1) - xi); xh = sph ? xi + h * amp : xi + h; }
+    if (j == 1) yl = fmaxf(1.0f, yj - 0.5f * (Y(2) - yj));
+    else yl = yj - 0.5f * (yj - Y(j - 1));
+    if (j == nj_dst) yh = fminf(1.0f * nj_src, yj + 0.5f * (yj - Y(j - 1)));
+    else yh = yj + 0.5f * (Y(j + 1) - yj);
+    int jstart, jend;
+    if (j == 1) {
+        jstart = f_ifix(yl); jend = f_nint(yh);
+        if ((float)jstart > yl) jstart = jstart - 1;
+    } else if (j == nj_dst) {
+        jstart = f_ifix(yj); jend = f_nint(yh);
+    } else {
+        jstart = f_ifix(yl); jend = f_nint(yh);
+        if ((0.5f + (float)jstart) < yl) jstart = jstart + 1;
+    }
+    int istart = f_ifix(xl), iend = f_nint(xh);
+    if ((0.5f + (float)istart) < xl) istart = istart + 1;
+    if (j == 1 && (float)iend < xh) iend = iend + 1;
+    AvgSrc src;
+    src.ni = ni_src; src.nj = nj_src; src.ext = a.src.ext;
+    for (int f = 0; f < a.nfields; f++) {
+        src.z = a.zin + (long)f * a.in_stride;
+        float acc = 0.0f, total_area = 0.0f;
+        for (int jj = jstart; jj <= jend; jj++) {
+            float ytile_min = (float)jj - 0.5f, ytile_max = (float)jj + 0.5f, yfrac = 1.0f;
+            if (j == 1) {
+                if (jj == 1) ytile_min = 1.0f;
+                yfrac = ytile_max - ytile_min;
+            } else if (j == nj_dst) {
+                if (jj == nj_src) ytile_max = (float)nj_src;
+                yfrac = ytile_max - ytile_min;
+            }
+            if (ytile_min < yl) yfrac = ytile_max - yl;
+            if (ytile_max > yh) yfrac = yh - ytile_min;
+            for (int ii = istart; ii <= iend; ii++) {
+                const float xtile_min = (float)ii - 0.5f, xtile_max = (float)ii + 0.5f;
+                float xfrac = 1.0f;
+                if (xtile_min < xl) xfrac = xtile_max - xl;
+                if (xtile_max > xh) xfrac = xh - xtile_min;
+                const float area = xfrac * yfrac;
+                total_area = total_area + area;
+                acc = acc + src(ii, jj) * area;
+            }
+        }
+        if (total_area != 0.0f) acc = acc / total_area;
+        a.zout[n + (long)f * a.out_stride] = acc;
+    }
+}
+
 // ez_corrbgd.inc:29-52: one thread per (field, pole row), sequential fp32 sum
 __global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -926,6 +1020,19 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
 void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s) {
     if (npts <= 0) return;
     k_zone_list<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(zb, npts, skip_dehors_only, list, cursor);
+}
+
+int interp_avg(const InterpArgs &a, const float *row_lat, int sph, const int *zlist, int nzlist, cudaStream_t s) {
+    if (a.npts <= 0 || a.nfields <= 0) return 0;
+    const int npts = a.band_j1 > 0 ? (a.band_j1 - a.band_j0) * a.out_ni : a.npts;
+    k_avg<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(a, row_lat, sph);
+    if (nzlist <= 0) return 1;
+    // ez_corrval.c:54-143 on the points with zone bits (k_interp_fast's average branch)
+    InterpArgs b = a;
+    b.list = zlist;
+    b.nlist = nzlist;
+    launch_fast(b, s);
+    return 2;
 }
 
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,

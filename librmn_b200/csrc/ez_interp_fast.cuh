@@ -334,6 +334,27 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
         }
         return;
     }
+    // interp_degree = average / sph_average: k_avg has written every point; ez_corrval.c:54-143 then rewrites the points outside
+    // the source (constant, or interpolated with extrap_degree) and, for scalars, the points at a pole.  Its polar-strip
+    // rewrites (ez_corrval_aunord.c:53-112, ez_corrval_ausud.c:64-129) have no case for these degrees and store an uninitialised
+    // work array in the reference: here those points keep their average.
+    if (a.o.degree == EZ_AVERAGE || a.o.degree == EZ_SPH_AVERAGE) {
+        for (int f = 0; f < nf; f++) {
+            bool write = false;
+            float v = 0.f;
+            if (zbits & ZB_DEHORS) {
+                if (a.o.extrap >= EZ_MAXIMUM) v = (a.o.vector || !a.fs) ? 0.0f : a.fs[f0 + f].fudge;
+                else v = interp_point(make_fetch(g, z + f * is, a.o.sym_sign), g, a.o.extrap, px, py);
+                write = true;
+            }
+            if (!a.o.vector && a.fs) {
+                if (zbits & ZB_POLE_NORD) { v = a.fs[f0 + f].pole_n; write = true; }
+                if (zbits & ZB_POLE_SUD) { v = a.fs[f0 + f].pole_s; write = true; }
+            }
+            if (write) zo[f * os] = v;
+        }
+        return;
+    }
     // outside the source with a constant extrapolation (ez_corrval.c:56-93: maximum / minimum / value; 0.0 for vectors, :64-67):
     // a plain store -- a LAM source leaves a third of a larger target here (C3), and DEHORS excludes the polar zones (ez_defzones.c:88-109)
     if (zbits == ZB_DEHORS && a.o.extrap >= EZ_MAXIMUM) {
@@ -516,6 +537,10 @@ bool launch_fast(const InterpArgs &a, cudaStream_t s) {
     const dim3 nb(nbx, a.list ? (a.nfields + LIST_LCH - 1) / LIST_LCH : 1);
     switch (a.o.degree) {
         case EZ_NEAREST: k_interp_fast<0><<<nb, TPB, 0, s>>>(a); return true;
+        case EZ_AVERAGE: case EZ_SPH_AVERAGE:   // zone points of an average only (interp_avg): the zone branch does not depend on DEG
+            if (!a.list) return false;
+            k_interp_fast<0><<<nb, TPB, 0, s>>>(a);
+            return true;
         case EZ_LINEAR:
             if (a.o.arith == 2) k_interp_fast<5><<<nb, TPB, 0, s>>>(a);
             else k_interp_fast<1><<<nb, TPB, 0, s>>>(a);

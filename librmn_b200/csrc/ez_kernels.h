@@ -117,6 +117,9 @@ struct DirectPre {
 };
 int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork = nullptr, const DirectPre *pre = nullptr);
 void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s);
+// interp_degree = average / sph_average (ez_avg.inc, ez_avg_sph.inc): every target point, then ez_corrval on the zone list.
+// row_lat: latitudes of the target points (first column read), sph_average only
+int interp_avg(const InterpArgs &a, const float *row_lat, int sph, const int *zlist, int nzlist, cudaStream_t s);
 // scattered targets: permutation of the target points by source cell, for gather locality in the per-point kernel
 bool sort_points_by_cell(const float *x, const float *y, const uint8_t *zb, int ni, int nj, int npts, int *perm, cudaStream_t s);
 // tiled path: is (degree, arith, source) eligible ; classification passes ; tile geometry

@@ -1584,8 +1584,101 @@ void ez_applywgts_(float *outfld, float *wts, fint *idxs, float *infld, float *x
     }
 }
 void ez_calcxy_y_m_(void) { off_path("ez_calcxy_y_m"); }
-void ez_avg_(void) { off_path("ez_avg"); }
-void ez_avg_sph_(void) { off_path("ez_avg_sph"); }
+/* ------------------------------------------------------------------------------------------------
+ * ez_avg.inc:1-170 and ez_avg_sph.inc:1-232 -- area-weighted box average of the source cells a target cell covers
+ * (interp_degree = average / sph_average, gdinterp.c:181-203,283-306).  One routine restates both: they differ only
+ * in the x extent of a target cell, widened by 1 / cos(latitude of the target row) in the spherical variant
+ * (ez_avg_sph.inc:65-90).  The target cell of point (i, j) runs half-way to its neighbours in the source index space
+ * taken from the FIRST row (x) and FIRST column (y) of the gridset coordinates (ez_avg.inc:55-56): the routine assumes
+ * axis-aligned grids.  All arithmetic is default real (fp32), sums in loop order.  ztmp(ii, jj) of the reference is the
+ * field replicated in x according to `extension` (ez_avg.inc:20-52); an index outside what the reference allocates and
+ * fills is undefined there and reads as 0 here. */
+static float avg_ztmp(const float *zin, int ni, int nj, int ext, int ii, int jj) {
+    if (jj < 1 || jj > nj) return 0.0f;
+    int i;
+    if (ext == 0) {
+        if (ii < 1 || ii > ni) return 0.0f;
+        i = ii;
+    } else if (ext == 1) {   /* filled: 2-ni .. 2ni-2 from zin(1 .. ni-1) */
+        if (ii < 2 - ni || ii > 2 * ni - 2) return 0.0f;
+        i = ii >= ni ? ii - ni + 1 : (ii >= 1 ? ii : ii + ni - 1);
+    } else {                 /* filled: 1-ni .. 2ni from zin(1 .. ni) */
+        if (ii < 1 - ni || ii > 2 * ni) return 0.0f;
+        i = ii > ni ? ii - ni : (ii >= 1 ? ii : ii + ni);
+    }
+    return zin[(long)(jj - 1) * ni + (i - 1)];
+}
+static void avg_common(float *zout, const float *xx, const float *yy, const float *lats_dst, int ni_dst, int nj_dst, const float *zin,
+                       int ni_src, int nj_src, int ext) {
+    const float degre_a_radian = 0.017453295199f;
+    float *x = (float *)malloc(sizeof(float) * ni_dst), *y = (float *)malloc(sizeof(float) * nj_dst);
+    float *y_low = (float *)malloc(sizeof(float) * nj_dst), *y_high = (float *)malloc(sizeof(float) * nj_dst);
+    for (int i = 0; i < ni_dst; i++) x[i] = xx[i];                       /* x = xx(:,1) */
+    for (int j = 0; j < nj_dst; j++) y[j] = yy[(long)j * ni_dst];        /* y = yy(1,:) */
+    if (x[0] > (float)(ni_src - 1)) x[0] = 1.0f;
+    y_low[0] = fmaxf(1.0f, y[0] - 0.5f * (y[1] - y[0]));
+    for (int j = 1; j < nj_dst; j++) y_low[j] = y[j] - 0.5f * (y[j] - y[j - 1]);
+    y_high[nj_dst - 1] = fminf(1.0f * nj_src, y[nj_dst - 1] + 0.5f * (y[nj_dst - 1] - y[nj_dst - 2]));
+    for (int j = 0; j < nj_dst - 1; j++) y_high[j] = y[j] + 0.5f * (y[j + 1] - y[j]);
+    for (int j = 1; j <= nj_dst; j++) {
+        float amp = 1.0f;
+        const int sph = lats_dst != NULL;
+        if (sph) amp = 1.0f / cosf(lats_dst[j - 1] * degre_a_radian);
+        const float yl = y_low[j - 1], yh = y_high[j - 1];
+        int jstart, jend;
+        if (j == 1) {                      /* "Moyenne 1e rangee" */
+            jstart = f_ifix(yl); jend = f_nint(yh);
+            if ((float)jstart > yl) jstart = jstart - 1;
+        } else if (j == nj_dst) {          /* "Moyenne rangee du haut" */
+            jstart = f_ifix(y[nj_dst - 1]); jend = f_nint(yh);
+        } else {
+            jstart = f_ifix(yl); jend = f_nint(yh);
+            if ((0.5f + (float)jstart) < yl) jstart = jstart + 1;
+        }
+        for (int i = 1; i <= ni_dst; i++) {
+            float xl, xh;
+            if (i == 1) xl = sph ? x[0] - 0.5f * (x[1] - x[0]) * amp : x[0] - 0.5f * (x[1] - x[0]);
+            else xl = sph ? x[i - 1] - 0.5f * (x[i - 1] - x[i - 2]) * amp : x[i - 1] - 0.5f * (x[i - 1] - x[i - 2]);
+            if (i == ni_dst) xh = sph ? x[i - 1] + 0.5f * (x[i - 1] - x[i - 2]) * amp : x[i - 1] + 0.5f * (x[i - 1] - x[i - 2]);
+            else xh = sph ? x[i - 1] + 0.5f * (x[i] - x[i - 1]) * amp : x[i - 1] + 0.5f * (x[i] - x[i - 1]);
+            float acc = 0.0f, total_area = 0.0f;
+            int istart = f_ifix(xl), iend = f_nint(xh);
+            if ((0.5f + (float)istart) < xl) istart = istart + 1;
+            if (j == 1 && (float)iend < xh) iend = iend + 1;
+            for (int jj = jstart; jj <= jend; jj++) {
+                float ytile_min = (float)jj - 0.5f, ytile_max = (float)jj + 0.5f, yfrac = 1.0f;
+                if (j == 1) {
+                    if (jj == 1) ytile_min = 1.0f;
+                    yfrac = ytile_max - ytile_min;
+                } else if (j == nj_dst) {
+                    if (jj == nj_src) ytile_max = (float)nj_src;
+                    yfrac = ytile_max - ytile_min;
+                }
+                if (ytile_min < yl) yfrac = ytile_max - yl;
+                if (ytile_max > yh) yfrac = yh - ytile_min;
+                for (int ii = istart; ii <= iend; ii++) {
+                    const float xtile_min = (float)ii - 0.5f, xtile_max = (float)ii + 0.5f;
+                    float xfrac = 1.0f;
+                    if (xtile_min < xl) xfrac = xtile_max - xl;
+                    if (xtile_max > xh) xfrac = xh - xtile_min;
+                    const float area = xfrac * yfrac;
+                    total_area = total_area + area;
+                    acc = acc + avg_ztmp(zin, ni_src, nj_src, ext, ii, jj) * area;
+                }
+            }
+            if (total_area != 0.0f) acc = acc / total_area;
+            zout[(long)(j - 1) * ni_dst + (i - 1)] = acc;
+        }
+    }
+    free(x); free(y); free(y_low); free(y_high);
+}
+void ez_avg_(float *zout, float *xx, float *yy, fint *ni_dst, fint *nj_dst, float *zin, fint *ni_src, fint *nj_src, fint *extension) {
+    avg_common(zout, xx, yy, NULL, *ni_dst, *nj_dst, zin, *ni_src, *nj_src, *extension);
+}
+void ez_avg_sph_(float *zout, float *xx, float *yy, float *lats_dst, fint *ni_dst, fint *nj_dst, float *zin, fint *ni_src, fint *nj_src,
+                 fint *extension) {
+    avg_common(zout, xx, yy, lats_dst, *ni_dst, *nj_dst, zin, *ni_src, *nj_src, *extension);
+}
 void ez_genpole_(void) { off_path("ez_genpole"); }
 void ez_llflamb_(void) { off_path("ez_llflamb"); }
 void ez_vtllfxy_(void) { off_path("ez_vtllfxy"); }

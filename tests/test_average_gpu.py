@@ -1,0 +1,123 @@
+"""interp_degree = average / sph_average (ez_avg.inc, ez_avg_sph.inc, dispatch gdinterp.c:118-131,181-203,283-306).
+The CUDA kernel repeats the Fortran's default-real arithmetic in its loop order without contraction: `average` must equal the
+oracle BIT FOR BIT; `sph_average` differs only through the rounding of the target rows' latitude (tolerance).  Points in the
+polar strips are left out of the comparison: the reference stores an uninitialised work array there (ez_corrval_aunord.c:53-112
+has no case for these degrees)."""
+import numpy as np
+import pytest
+
+from librmn_b200 import configs
+from test_parity_gpu import TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs(lib):
+    """(name, gdin, gdout, src_shape, dst_shape, src lat, src lon)"""
+    out = []
+    def ll(ni, nj, lat0, lon0, dlat, dlon):
+        lon, lat = np.meshgrid(lon0 + dlon * np.arange(ni), lat0 + dlat * np.arange(nj))
+        return lat, lon
+    g_glb = configs.def_L(lib, 360, 181, -90.0, 0.0, 1.0, 1.0)
+    la, lo = ll(360, 181, -90.0, 0.0, 1.0, 1.0)
+    out.append(("global1deg_to_5deg", g_glb, configs.def_L(lib, 60, 25, -60.0, 10.0, 5.0, 5.0), (181, 360), (25, 60), la, lo))
+    out.append(("global1deg_to_global4deg_poles", g_glb, configs.def_L(lib, 90, 46, -90.0, 0.0, 4.0, 4.0), (181, 360), (46, 90), la, lo))
+    out.append(("global1deg_to_2.5deg_seam", g_glb, configs.def_L(lib, 144, 60, -73.75, 1.25, 2.5, 2.5), (181, 360), (60, 144), la, lo))
+    g_reg = configs.def_L(lib, 200, 150, 20.0, 250.0, 0.25, 0.25)
+    la, lo = ll(200, 150, 20.0, 250.0, 0.25, 0.25)
+    out.append(("regional_to_1deg_inside", g_reg, configs.def_L(lib, 30, 20, 25.0, 255.0, 1.0, 1.0), (150, 200), (20, 30), la, lo))
+    out.append(("regional_to_1.3deg_outside", g_reg, configs.def_L(lib, 50, 40, 15.0, 245.0, 1.3, 1.3), (150, 200), (40, 50), la, lo))
+    g_gau = lib.ezqkdef(192, 96, "G", 0, 0, 0, 0)
+    lat = np.zeros((96, 192), np.float32); lon = np.zeros((96, 192), np.float32)
+    lib.gdll(g_gau, lat, lon)
+    out.append(("gaussian_to_6deg", g_gau, configs.def_L(lib, 50, 20, -57.0, 20.0, 6.0, 6.0), (96, 192), (20, 50), lat.astype(np.float64), lon.astype(np.float64)))
+    return out
+
+
+def _set(lib, degree, extrap=None, value=None):
+    lib.ezsetopt("interp_degree", degree)
+    lib.ezsetopt("extrap_degree", extrap or "maximum")
+    if value is not None:
+        lib.ezsetval("extrap_value", value)
+
+
+@pytest.mark.parametrize("degree", ["average", "sph_average"])
+def test_average_against_oracle(ezb, ezref, cuda_ok, degree):
+    try:
+        for (pb, pr) in zip(_pairs(ezb), _pairs(ezref)):
+            name, gdin_b, gdout_b, ss, ds, la, lo = pb
+            for extrap, value in ((None, None), ("value", -7.5), ("linear", None)):
+                outs = []
+                zin = configs.field(la, lo, k=2).astype(np.float32).reshape(ss)
+                for lib, p in ((ezb, pb), (ezref, pr)):
+                    _set(lib, degree, extrap, value)
+                    assert lib.ezdefset(p[2], p[1]) == 1
+                    z = np.full(ds, -999.0, np.float32)
+                    rc = lib.ezsint(z, zin)
+                    outs.append((rc, z))
+                (rc_b, zb_), (rc_r, zr) = outs
+                assert rc_b == rc_r, (name, extrap, rc_b, rc_r)
+                assert ezb.last_path()[0] & 32, "averaging kernel not taken"
+                x, y, zbits, counts = ezb.get_gridset(gdout_b, gdin_b, ds[0] * ds[1])
+                keep = ((zbits & 0x06) == 0).reshape(ds)      # not in a polar strip (undefined in the reference)
+                rng = float(zin.max() - zin.min())
+                d = np.abs(zb_.astype(np.float64) - zr)[keep]
+                nbit = int((zb_[keep] != zr[keep]).sum())
+                print("%-34s %-11s extrap=%-7s rc=%d zones=%s max|d|/range=%.2e bit-diff=%d/%d" % (name, degree, extrap, rc_b, counts[:5].tolist(), d.max() / rng, nbit, int(keep.sum())))
+                if degree == "average":
+                    assert nbit == 0, (name, extrap, nbit)
+                else:
+                    assert d.max() < TOL * rng, (name, extrap, d.max() / rng)
+    finally:
+        for lib in (ezb, ezref):
+            _set(lib, "cubic", "maximum")
+
+
+def test_average_batch_band_and_vectors(ezb, ezref, cuda_ok):
+    """Several fields in one call, an output-row band, and c_ezuvint under `average` (components averaged, then rotated)."""
+    try:
+        (name, gdin, gdout, ss, ds, la, lo) = _pairs(ezb)[3]
+        (_, gdin_r, gdout_r, _, _, _, _) = _pairs(ezref)[3]
+        for lib, a, b in ((ezb, gdout, gdin), (ezref, gdout_r, gdin_r)):
+            _set(lib, "average")
+            assert lib.ezdefset(a, b) == 1
+        zin = np.stack([configs.field(la, lo, k=k).astype(np.float32).reshape(ss) for k in range(5)])
+        batch = np.zeros((5,) + ds, np.float32)
+        assert ezb.ezsint_batch(batch, zin, 5) >= 0
+        for k in range(5):
+            ref = np.zeros(ds, np.float32)
+            ezref.ezsint(ref, zin[k])
+            assert np.array_equal(batch[k], ref), k
+        ezb.set_rows(3, 11)
+        try:
+            band = np.zeros((5, 8, ds[1]), np.float32)
+            assert ezb.ezsint_batch(band, zin, 5) >= 0
+        finally:
+            ezb.set_rows()
+        assert np.array_equal(band, batch[:, 3:11])
+        u, v = configs.wind_fields(la, lo, 1)
+        u = u.reshape(ss).astype(np.float32); v = v.reshape(ss).astype(np.float32)
+        res = []
+        for lib in (ezb, ezref):
+            uo, vo = np.zeros(ds, np.float32), np.zeros(ds, np.float32)
+            assert lib.ezuvint(uo, vo, u, v) >= 0
+            res.append((uo, vo))
+        rng = float(max(u.max() - u.min(), v.max() - v.min()))
+        assert max(np.abs(res[0][0].astype(np.float64) - res[1][0]).max(), np.abs(res[0][1].astype(np.float64) - res[1][1]).max()) < TOL * rng
+        # a target that is not L / A / B / G: the reference announces it and interpolates linearly (gdinterp.c:118-131)
+        gps = ezb.ezqkdef(40, 40, "N", *ezb.cxgaig("N", 20.5, 20.5, 200000.0, 10.0), 0) if hasattr(ezb, "cxgaig") else None
+        if gps is not None and gps >= 0:
+            gps_r = ezref.ezqkdef(40, 40, "N", *ezref.cxgaig("N", 20.5, 20.5, 200000.0, 10.0), 0)
+            g1 = configs.def_L(ezb, 360, 181, -90.0, 0.0, 1.0, 1.0); g1r = configs.def_L(ezref, 360, 181, -90.0, 0.0, 1.0, 1.0)
+            lon2, lat2 = np.meshgrid(np.arange(360.0), np.arange(181.0) - 90.0)
+            z1 = configs.field(lat2, lon2, k=0).astype(np.float32)
+            o = []
+            for lib, a, b in ((ezb, gps, g1), (ezref, gps_r, g1r)):
+                assert lib.ezdefset(a, b) == 1
+                zz = np.zeros((40, 40), np.float32)
+                assert lib.ezsint(zz, z1) >= 0
+                o.append(zz)
+            assert np.abs(o[0].astype(np.float64) - o[1]).max() < TOL * float(z1.max() - z1.min())
+    finally:
+        for lib in (ezb, ezref):
+            _set(lib, "cubic", "maximum")

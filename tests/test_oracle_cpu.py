@@ -248,3 +248,41 @@ def test_oracle_matches_golden_vectors(ezref):
             worst = max(worst, d)
             assert d < 2e-6, "%s drifted by %g of range" % (c.name, d)
     assert worst >= 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# interp_degree = average / sph_average (ez_avg.inc, ez_avg_sph.inc restated in oracle/fortran_shim.c)
+# ---------------------------------------------------------------------------------------------------
+def test_average_preserves_constants_and_means(ezref):
+    """Pins of the box-average leaf: a constant field stays constant; at an exact 4:1 coarsening whose target cells are made of
+    whole source cells plus half cells on their rim, the result is that weighted mean (computed here independently in numpy);
+    sph_average at the equator row equals average (1 / cos(0) = 1)."""
+    from librmn_b200 import configs
+    try:
+        ezref.ezsetopt("interp_degree", "average")
+        gdin = configs.def_L(ezref, 360, 181, -90.0, 0.0, 1.0, 1.0)
+        gdout = configs.def_L(ezref, 40, 21, -40.0, 20.0, 4.0, 4.0)
+        assert ezref.ezdefset(gdout, gdin) == 1
+        z = np.full((181, 360), 3.25, np.float32)
+        o = np.zeros((21, 40), np.float32)
+        assert ezref.ezsint(o, z) >= 0
+        assert np.array_equal(o, np.full_like(o, 3.25))
+        lon, lat = np.meshgrid(np.arange(360.0), np.arange(181.0) - 90.0)
+        z = configs.field(lat, lon, k=1).astype(np.float32)
+        assert ezref.ezsint(o, z) >= 0
+        # interior target point (i, j): centre at source index (x, y) = (21 + 4 i, 51 + 4 j) (1-based), cell = +-2 source cells:
+        # three whole cells and two half cells per axis
+        w = np.array([0.5, 1.0, 1.0, 1.0, 0.5])
+        zz = z.astype(np.float64)
+        for (i, j) in ((3, 4), (17, 10), (30, 15)):
+            ci, cj = 20 + 4 * i, 50 + 4 * j      # 0-based centre
+            box = zz[cj - 2:cj + 3, ci - 2:ci + 3]
+            want = (box * np.outer(w, w)).sum() / 16.0
+            assert abs(o[j, i] - want) < 2e-5 * abs(want), (i, j, o[j, i], want)
+        ezref.ezsetopt("interp_degree", "sph_average")
+        o2 = np.zeros_like(o)
+        assert ezref.ezsint(o2, z) >= 0
+        assert np.array_equal(o2[10], o[10])          # target row 10 lies on the equator
+        assert not np.array_equal(o2[18], o[18])      # 32 N: cells 1 / cos(32 deg) wider
+    finally:
+        ezref.ezsetopt("interp_degree", "cubic")
