@@ -445,6 +445,18 @@ def measure(B, name, arith, steps, warmup, levels, rank, world, stream, sampler_
                     "step": {"algorithmic_bytes": abytes, "ms": step_kern_ms, "achieved": abytes / (step_kern_ms * 1e-3) / 1e9,
                              "frac": abytes / (step_kern_ms * 1e-3) / 1e9 / peak},
                     "points_on_per_point_list": nlist}
+    elif kms and (path & 16):
+        # direct kernel (calls of 1-4 fields): [scalars pre-pass | direct kernel | zone-list kernel], timed in line; in the timed
+        # steps the two small kernels run beside the direct kernel on a forked stream
+        pre_ms, dir_ms, zl_ms = [statistics.median(k[i] for k in kms) for i in range(3)]
+        dom = "k_interp_direct<%d>" % deg
+        achieved = abytes / (dir_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_kind": peak_kind, "kernel": dom, "kernel_ms": dir_ms, "algorithmic_bytes_per_launch": abytes,
+                    "kernels": {"k_field_scalars": {"ms": pre_ms}, dom: {"ms": dir_ms, "frac": achieved / peak}, "k_interp_fast (zone list)": {"ms": zl_ms, "points": nlist}},
+                    "step": {"algorithmic_bytes": abytes, "ms": step_kern_ms, "achieved": abytes / (step_kern_ms * 1e-3) / 1e9,
+                             "frac": abytes / (step_kern_ms * 1e-3) / 1e9 / peak},
+                    "points_on_per_point_list": nlist}
     else:
         achieved = abytes / (step_kern_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -558,7 +570,7 @@ def main():
 
     extra = {}
     if full and world == 1 and args.workload == "c2" and args.arith == 2 and not args.levels:
-        for key, (wl, ar) in (("c3_ezuvint", ("c3", 2)), ("c5", ("c5", 2)), ("c2_arith1_fp64", ("c2", 1))):
+        for key, (wl, ar) in (("c3_ezuvint", ("c3", 2)), ("c1_ezsint", ("c1", 2)), ("c5", ("c5", 2)), ("c2_arith1_fp64", ("c2", 1))):
             try:
                 extra[key] = sub_record(measure(B, wl, ar, args.steps, args.warmup, 0, rank, world, stream, sustain_s=0.5, pageable=(wl != "c2"), parity=True))
             except SystemExit as ex:

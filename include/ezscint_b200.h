@@ -36,6 +36,15 @@ int32_t ezuvint_(float *uuout, float *vvout, float *uuin, float *vvin);         
 int32_t c_ezwdint(float *spdout, float *wdout, float *uuin, float *vvin);          /* ref :93  (ezwdint.c:36) */
 int32_t ezwdint_(float *spdout, float *wdout, float *uuin, float *vvin);           /* ref :92 */
 int     c_ezsint_mask(int *mask_out, int *mask_in);                                /* ref :164 (ez_mask.c:184) */
+/* masked interpolation (ez_mask.c:127-181): c_ezsint / c_ezuvint, the mask transfer, then every target point whose transferred mask
+ * is 0 takes the minimum of the interpolated field (lorenzo_mask_fill.inc, methode 2).  Not for 'U' grids.  c_ezsint_m / c_ezuvint_m
+ * only print "currently not implemented", as in the reference (ez_mask.c:114-124). */
+int     c_ezsint_mdm(float *zout, int *mask_out, float *zin, int *mask_in);                                   /* ref :158 */
+int     c_ezuvint_mdm(float *uuout, float *vvout, int *mask_out, float *uuin, float *vvin, int *mask_in);     /* ref :161 */
+int     ezsint_mdm_(float *zout, int *mask_out, float *zin, int *mask_in);                                    /* ref :157 */
+int     ezuvint_mdm_(float *uuout, float *vvout, int *mask_out, float *uuin, float *vvin, int *mask_in);      /* ref :160 */
+int     c_ezsint_m(float *zout, float *zin);                                                                  /* ref :152 */
+int     c_ezuvint_m(float *uuout, float *vvout, float *uuin, float *vvin);                                    /* ref :155 */
 int     ezsint_mask_(int *mask_out, int *mask_in);                                 /* ref :163 */
 
 /* ---- options ---------------------------------------------------------------------------------- */
@@ -147,6 +156,7 @@ int32_t c_ezb200_last_path(int32_t *nlist);
 /* Measurement aid: with timing on, every tiled interpolation launch records CUDA events on the session stream around its
  * kernels; c_ezb200_last_kernel_ms returns ms[3] = {row-separable tile kernel, window tile kernel, per-point list kernel}
  * of the LAST launch and tiles[3] = {tiles on the row-separable kernel, tiles on the window kernel, points on the list}.
+ * After a direct-kernel launch (c_ezb200_last_path bit 4): ms[3] = {per-field scalars pre-pass, direct kernel, zone-list kernel}.
  * Returns -1 when the last launch was not timed. */
 int32_t c_ezb200_set_timing(int32_t on);
 int32_t c_ezb200_last_kernel_ms(float *ms, int32_t *tiles);

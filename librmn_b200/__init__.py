@@ -251,6 +251,15 @@ class EzLib:
     def ezsint_mask(self, mask_out, mask_in):
         return self.lib.c_ezsint_mask(_ptr(mask_out), _ptr(mask_in))
 
+    def ezsint_mdm(self, zout, mask_out, zin, mask_in):
+        _check_f32(zout, zin)
+        return self.lib.c_ezsint_mdm(C.c_void_p(_ptr(zout)), C.c_void_p(_ptr(mask_out)), C.c_void_p(_ptr(zin)), C.c_void_p(_ptr(mask_in)))
+
+    def ezuvint_mdm(self, uuout, vvout, mask_out, uuin, vvin, mask_in):
+        _check_f32(uuout, vvout, uuin, vvin)
+        p = [C.c_void_p(_ptr(a)) for a in (uuout, vvout, mask_out, uuin, vvin, mask_in)]
+        return self.lib.c_ezuvint_mdm(*p)
+
     # ---- additive (libezb200 only) -----------------------------------------------------------
     def ezsint_batch(self, zout, zin, nfields):
         _check_f32(zout, zin)

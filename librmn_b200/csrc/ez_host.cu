@@ -1230,7 +1230,8 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.zout = zo;
         }
         a.wrot = (wrot && nfields == 2) ? wrot : nullptr;
-        S.launches += ezk::interp_direct(a, zl, nz, S.stream, ensure_fork() ? &S.fork : nullptr, &pre);
+        const bool timed_direct = S.timing && S.tev.ev[0];
+        S.launches += ezk::interp_direct(a, zl, nz, S.stream, ensure_fork() ? &S.fork : nullptr, &pre, timed_direct ? &S.tev : nullptr);
         if (a.wrot) {
             if (nz > 0) {
                 ezk::wind_apply_list(a.wrot, zo, zo + out_stride, 0, 1, zl, nz, band.j0 * out.ni, band.j1 * out.ni, S.stream);
@@ -1241,7 +1242,7 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
         S.last_path = 16 | (nz > 0 ? 4 : 0);
         S.last_nlist = nz;
         S.last_tiles[0] = S.last_tiles[1] = S.last_tiles[2] = 0;
-        S.timing_valid = false;
+        S.timing_valid = timed_direct;
         if (!gs->yy && S.opt.polar_correction == 1 && !vector && rc >= 0 && (in.grtyp == 'Z' || in.grtyp == '#') && in.grref == 'E' && out.grtyp == 'B') {
             if (band.on) {
                 fprintf(stderr, "<ezb200> output-row bands are not supported for 'B' targets fed from a rotated source (pole rows are averaged over the whole row set)\n");
@@ -2723,6 +2724,64 @@ int c_ezsint_mask(int *mask_out, int *mask_in) {   // ez_mask.c:184-223
     return 0;
 }
 int ezsint_mask_(int *mask_out, int *mask_in) { return c_ezsint_mask(mask_out, mask_in); }
+
+// lorenzo_mask_fill(fld, mask, ni, nj, 2) on a caller array (host or device pointers)
+static int mask_fill_any(float *fld, int *mask, size_t n) {
+    Lock lk;
+    unsigned int *scr = (unsigned int *)S.st_scratch.get(2 * sizeof(unsigned int));
+    if (!scr) return -1;
+    const bool df = is_device_ptr(fld), dm = is_device_ptr(mask);
+    float *d_f = df ? fld : (float *)S.st_out[0].get(n * sizeof(float));
+    int *d_m = dm ? mask : (int *)S.st_in[0].get(n * sizeof(int));
+    if (!d_f || !d_m) return -1;
+    if (!df) CUDA_OK(cudaMemcpyAsync(d_f, fld, n * sizeof(float), cudaMemcpyHostToDevice, S.stream));
+    if (!dm) CUDA_OK(cudaMemcpyAsync(d_m, mask, n * sizeof(int), cudaMemcpyHostToDevice, S.stream));
+    ezk::mask_fill_min(d_f, d_m, (long)n, scr, S.stream);
+    S.launches += 3;
+    CUDA_OK(cudaGetLastError());
+    if (!df) {
+        CUDA_OK(cudaMemcpyAsync(fld, d_f, n * sizeof(float), cudaMemcpyDeviceToHost, S.stream));
+        CUDA_OK(cudaStreamSynchronize(S.stream));
+    }
+    return 0;
+}
+static int mdm_grids(const char *who, size_t *nout) {
+    Lock lk;
+    if (!session_ok(who)) return -1;
+    Grid &in = *grid_of(S.gdin), &out = *grid_of(S.gdout);
+    if (in.nsubgrids > 0 || out.nsubgrids > 0) {
+        fprintf(stderr, "<%s> This operation is not supported for 'U' grids.\n", who);
+        return -1;
+    }
+    *nout = (size_t)out.ni * out.nj;
+    return 0;
+}
+// ez_mask.c:127-152: c_ezsint, the mask transfer, then the masked-out target points take the field's minimum
+int32_t c_ezsint_mdm(float *zout, int *mask_out, float *zin, int *mask_in) {
+    size_t nout = 0;
+    if (mdm_grids("ezsint_mdm", &nout) < 0) return -1;
+    if (ezsint_n(zout, zin, 1) < 0 || c_ezsint_mask(mask_out, mask_in) < 0) return -1;
+    return mask_fill_any(zout, mask_out, nout) < 0 ? -1 : 0;
+}
+// ez_mask.c:155-181
+int32_t c_ezuvint_mdm(float *uuout, float *vvout, int *mask_out, float *uuin, float *vvin, int *mask_in) {
+    size_t nout = 0;
+    if (mdm_grids("ezuvint_mdm", &nout) < 0) return -1;
+    if (c_ezsint_mask(mask_out, mask_in) < 0 || ezuvint_n(uuout, vvout, uuin, vvin, 1, 0) < 0) return -1;
+    if (mask_fill_any(uuout, mask_out, nout) < 0 || mask_fill_any(vvout, mask_out, nout) < 0) return -1;
+    return 0;
+}
+int32_t ezsint_mdm_(float *zout, int *mask_out, float *zin, int *mask_in) { return c_ezsint_mdm(zout, mask_out, zin, mask_in); }
+int32_t ezuvint_mdm_(float *uuout, float *vvout, int *mask_out, float *uuin, float *vvin, int *mask_in) {
+    return c_ezuvint_mdm(uuout, vvout, mask_out, uuin, vvin, mask_in);
+}
+// ez_mask.c:114-124: announced as not implemented by the reference itself
+int32_t c_ezsint_m(float *zout, float *zin) { (void)zout; (void)zin; fprintf(stderr, "<ezsint_m> This operation is currently not implemented.\n"); return 0; }
+int32_t c_ezuvint_m(float *uuout, float *vvout, float *uuin, float *vvin) {
+    (void)uuout; (void)vvout; (void)uuin; (void)vvin;
+    fprintf(stderr, "<ezuvint_m> This operation is currently not implemented.\n");
+    return 0;
+}
 
 int32_t c_ezb200_get_gridset(int32_t gdout, int32_t gdin, float *x, float *y, uint8_t *zonebits, int32_t *counts) {
     Lock lk;

@@ -755,6 +755,19 @@ __global__ void __launch_bounds__(TPB) k_avg(const __grid_constant__ InterpArgs 
     }
 }
 
+// lorenzo_mask_fill.inc:15-16,43-51 with methode = 2 (the only one c_ezsint_mdm / c_ezuvint_mdm use, ez_mask.c:127-181):
+// rmin = minval(fld) over the whole field, then fld = rmin wherever the transferred mask is 0
+__global__ void __launch_bounds__(TPB) k_field_min(const float *__restrict__ fld, long n, unsigned int *__restrict__ ordmin) {
+    float mn = INFINITY;
+    for (long k = (long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long)gridDim.x * TPB) mn = fminf(mn, fld[k]);
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(ordmin, f2ord(mn));
+}
+__global__ void __launch_bounds__(TPB) k_mask_fill(float *__restrict__ fld, const int *__restrict__ mask, long n, const unsigned int *__restrict__ ordmin) {
+    const long k = (long)blockIdx.x * TPB + threadIdx.x;
+    if (k < n && mask[k] == 0) fld[k] = ord2f(*ordmin);
+}
+
 // ez_corrbgd.inc:29-52: one thread per (field, pole row), sequential fp32 sum
 __global__ void k_corrbgd(float *zout, long stride, int nfields, int ni, int nj, int hem) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -978,7 +991,8 @@ int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, cons
     return 1;
 }
 
-int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork, const DirectPre *pre) {
+int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork, const DirectPre *pre,
+                  const InterpTiming *timing) {
     if (a.npts <= 0 || a.nfields <= 0) return 0;
     const int npts = a.band_j1 > 0 ? (a.band_j1 - a.band_j0) * a.out_ni : a.npts;
     int launches = 0;
@@ -986,8 +1000,9 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
     // launches: with fork resources they run beside the direct kernel (disjoint target points) instead of around it.  A
     // constant extrapolation value is read by the direct kernel itself: then the scalars stay in front of it.
     const bool direct_reads_fs = a.fs && !a.o.vector && a.o.extrap >= EZ_MAXIMUM;
-    const bool conc = fork && nzlist > 0 && !direct_reads_fs;
+    const bool conc = fork && !timing && nzlist > 0 && !direct_reads_fs;   // (per-kernel timing: everything in line on s)
     cudaStream_t s_list = s;
+    if (timing) cudaEventRecord(timing->ev[0], s);
     if (conc) {
         cudaEventRecord(fork->ev_fork, s);
         s_list = fork->aux[1];
@@ -997,6 +1012,7 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
         field_scalars(a, pre->need_poles, pre->need_minmax, pre->fs, pre->scratch, conc ? s_list : s);
         launches += pre->need_minmax ? 3 : 1;
     }
+    if (timing) cudaEventRecord(timing->ev[1], s);
     if (a.o.degree == EZ_CUBIC) {
         constexpr int per = TPB * DirectCfg<3>::PPT;
         k_interp_direct<3><<<(npts + per - 1) / per, TPB, 0, s>>>(a);
@@ -1005,6 +1021,7 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
         k_interp_direct<1><<<(npts + per - 1) / per, TPB, 0, s>>>(a);
     }
     launches++;
+    if (timing) cudaEventRecord(timing->ev[2], s);
     if (nzlist > 0) {
         InterpArgs b = a;
         b.list = zlist;
@@ -1013,6 +1030,7 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
         launch_fast(b, s_list);
         launches++;
     }
+    if (timing) cudaEventRecord(timing->ev[3], s);
     if (conc) { cudaEventRecord(fork->ev_join[1], s_list); cudaStreamWaitEvent(s, fork->ev_join[1], 0); }
     return launches;
 }
@@ -1033,6 +1051,15 @@ int interp_avg(const InterpArgs &a, const float *row_lat, int sph, const int *zl
     b.nlist = nzlist;
     launch_fast(b, s);
     return 2;
+}
+
+void mask_fill_min(float *fld, const int *mask, long n, unsigned int *scratch, cudaStream_t s) {
+    if (n <= 0) return;
+    k_minmax_init<<<1, 32, 0, s>>>(scratch, 1);   // scratch[0] = "no minimum yet"
+    int nb = (int)((n + (long)TPB * 8 - 1) / ((long)TPB * 8));
+    if (nb > 592) nb = 592;
+    k_field_min<<<nb, TPB, 0, s>>>(fld, n, scratch);
+    k_mask_fill<<<(unsigned int)((n + TPB - 1) / TPB), TPB, 0, s>>>(fld, mask, n, scratch);
 }
 
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,

@@ -115,7 +115,9 @@ struct DirectPre {
     FieldScalars *fs;
     unsigned int *scratch;
 };
-int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork = nullptr, const DirectPre *pre = nullptr);
+// timing (c_ezb200_set_timing): events around [scalars pre-pass | direct kernel | zone-list kernel], all in line on s
+int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork = nullptr, const DirectPre *pre = nullptr,
+                  const InterpTiming *timing = nullptr);
 void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s);
 // interp_degree = average / sph_average (ez_avg.inc, ez_avg_sph.inc): every target point, then ez_corrval on the zone list.
 // row_lat: latitudes of the target points (first column read), sph_average only
@@ -137,6 +139,8 @@ int cloud_apply(const int *idx, const float *wts, const int *mask, int nw, const
 // K19 integer mask transfer
 void mask_transfer(const float *x, const float *y, const int *mask_in, int *mask_out, int ni_out, int nj_out, int ni_in, int nj_in,
                    int linear, cudaStream_t s);
+// lorenzo_mask_fill (methode 2): fld = minval(fld) wherever mask == 0 ; scratch: 2 words
+void mask_fill_min(float *fld, const int *mask, long n, unsigned int *scratch, cudaStream_t s);
 // K17 wind rotation
 void wind(const WindArgs &a, cudaStream_t s);
 // cached per-point rotation of the (u,v) -> (u,v) conversion: build once per gridset, apply per call

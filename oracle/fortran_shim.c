@@ -1682,7 +1682,51 @@ void ez_avg_sph_(float *zout, float *xx, float *yy, float *lats_dst, fint *ni_ds
 void ez_genpole_(void) { off_path("ez_genpole"); }
 void ez_llflamb_(void) { off_path("ez_llflamb"); }
 void ez_vtllfxy_(void) { off_path("ez_vtllfxy"); }
-void lorenzo_mask_fill_(void) { off_path("lorenzo_mask_fill"); }
+/* lorenzo_mask_fill.inc:1-81 (c_ezsint_mdm / c_ezuvint_mdm, ez_mask.c:127-181, call it with methode = 2) */
+void lorenzo_mask_fill_(float *fld, fint *masque, fint *pni, fint *pnj, fint *methode) {
+    const int ni = *pni, nj = *pnj;
+#define FLD(i, j) fld[(long)((j) - 1) * ni + ((i) - 1)]
+#define MSK(i, j) masque[(long)((j) - 1) * ni + ((i) - 1)]
+    float rmin = fld[0], rmax = fld[0];
+    for (long k = 1; k < (long)ni * nj; k++) { if (fld[k] < rmin) rmin = fld[k]; if (fld[k] > rmax) rmax = fld[k]; }
+    switch (*methode) {
+        case 1:
+            for (int j = 2; j <= nj; j++)
+                for (int i = 2; i <= ni; i++)
+                    if (MSK(i, j) == 0) {
+                        FLD(i, j) = FLD(i - 1, j) + FLD(i, j - 1) - FLD(i - 1, j - 1);
+                        if (FLD(i, j) < rmin) FLD(i, j) = rmin;
+                        if (FLD(i, j) > rmax) FLD(i, j) = rmax;
+                    }
+            break;
+        case 2:
+            for (int j = 1; j <= nj; j++)
+                for (int i = 1; i <= ni; i++)
+                    if (MSK(i, j) == 0) FLD(i, j) = rmin;
+            break;
+        case 3:
+            for (int j = 1; j <= nj; j++) {
+                int i = 1, last_i = 1;
+                if (MSK(i, j) == 0) {
+                    for (;;) {
+                        i = i + 1;
+                        if (MSK(i, j) != 0) break;
+                        if (i == ni) { for (int k = 1; k <= ni; k++) FLD(k, j) = rmin; break; }
+                    }
+                    if (i < ni) for (int ii = last_i; ii <= i - 1; ii++) FLD(ii, j) = FLD(i, j);
+                }
+                for (;;) {
+                    i = i + 1;
+                    if (i >= ni + 1) break;
+                    if (MSK(i, j) == 0) FLD(i, j) = FLD(last_i, j);
+                    last_i = i;
+                }
+            }
+            break;
+    }
+#undef FLD
+#undef MSK
+}
 void qqq_ezget_mask_zones_(void) { off_path("qqq_ezget_mask_zones"); }
 int fstluk_(void) { off_path("fstluk"); return -1; }
 int fstprm_(void) { off_path("fstprm"); return -1; }

@@ -280,6 +280,47 @@ def test_mask_transfer_matches_oracle(ezb, ezref, cuda_ok):
         assert set(np.unique(res[0])) <= {0, 1}
 
 
+def test_masked_interpolation_mdm_matches_oracle(ezb, ezref, cuda_ok):
+    """c_ezsint_mdm / c_ezuvint_mdm (ez_mask.c:127-181): interpolation, mask transfer, then lorenzo_mask_fill methode 2 -- the
+    masked-out target points take the minimum of the interpolated field.  Host and device pointers."""
+    import torch
+    for vec in (False, True):
+        res = []
+        for lib in (ezb, ezref):
+            c = configs.c3(lib, scale=32, degree="linear")
+            c.defset()
+            rs = np.random.default_rng(11)
+            mask_in = (rs.uniform(size=c.src_shape) > 0.3).astype(np.int32)
+            mask_out = np.full(c.dst_shape, -1, np.int32)
+            if vec:
+                u, v = c.source_uv()
+                uo, vo = np.zeros(c.dst_shape, np.float32), np.zeros(c.dst_shape, np.float32)
+                assert lib.ezuvint_mdm(uo, vo, mask_out, u, v, mask_in) == 0
+                res.append((mask_out, uo, vo))
+            else:
+                z = np.zeros(c.dst_shape, np.float32)
+                zin = c.source_uv()[0]
+                assert lib.ezsint_mdm(z, mask_out, zin, mask_in) == 0
+                res.append((mask_out, z))
+        xr, yr = oracle_xy(ezref, c)
+        ex, ey = coord_eps(c, xr, yr)
+        tie = (near_half(xr, ex) | near_half(yr, ey) | near_int(xr, ex) | near_int(yr, ey)).reshape(c.dst_shape)
+        assert not ((res[0][0] != res[1][0]) & ~tie).any()
+        same_mask = res[0][0] == res[1][0]
+        for fb, fr in zip(res[0][1:], res[1][1:]):
+            rng = float(fr.max() - fr.min())
+            d = np.abs(fb.astype(np.float64) - fr)[same_mask]
+            assert d.max() < TOL * rng, (vec, d.max() / rng)
+            assert np.all(fb[res[0][0] == 0] == fb.min())        # filled with the field's minimum
+        if not vec:   # device pointers give the same answer
+            c = configs.c3(ezb, scale=32, degree="linear")
+            c.defset()
+            dz = torch.zeros(c.dst_shape, device="cuda"); dm = torch.full(c.dst_shape, -1, dtype=torch.int32, device="cuda")
+            assert ezb.ezsint_mdm(dz, dm, torch.from_numpy(zin).cuda(), torch.from_numpy(mask_in).cuda()) == 0
+            torch.cuda.synchronize()
+            assert np.array_equal(dz.cpu().numpy(), res[0][1]) and np.array_equal(dm.cpu().numpy(), res[0][0])
+
+
 # ---------------------------------------------------------------------------------------------------
 # the shared-memory tiled kernel (arith = 2, the default) at sizes where whole tiles take it
 # ---------------------------------------------------------------------------------------------------
