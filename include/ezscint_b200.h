@@ -73,11 +73,19 @@ int32_t gdgaxes_(int32_t *gdid, float *ax, float *ay);                          
 int32_t c_gdxpncf(int32_t gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2);   /* ref :117 (gdxpncf.c:33) logical index range */
 int32_t gdxpncf_(int32_t *gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2);   /* ref :116 */
 int32_t c_ezgdef(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4,
-                 float *ax, float *ay);                                            /* ref :15  (ezgdef.c:50); "FILE" sources -> -1 */
+                 float *ax, float *ay);                                            /* ref :15  (ezgdef.c:50); "FILE" sources -> c_ezgdef_ffile */
 int32_t ezgdef_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4,
                 float *ax, float *ay, F2Cl lengrtyp, F2Cl lengrref);               /* ref :13 */
 int32_t c_ezqkdef(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit);
-                                                                                   /* ref :66  (ezqkdef.c:25); regular types only, '#','Y','Z','U' need an FST file -> -1 */
+                                                                                   /* ref :66  (ezqkdef.c:25) = c_ezgdef_ffile */
+/* Grids defined by positional records ('>>', '^^', '^>') of an RPN standard file: grid types '#', 'Y', 'Z', 'U', ' '
+ * (ezgdef_ffile.c:29-140, ez_lireEnrPositionnels.c:12-349).  The records are located and read through the FST layer of the process
+ * -- c_fstinf / c_fstsui / c_fstprm / c_fstluk of the librmn that opened `iunit`, found with dlsym at the first such call, or
+ * handed over with c_ezb200_set_fst_hooks (same signatures as rmn/fstd98.h:42-67).  Without them these grid types fail with -1. */
+int32_t c_ezgdef_ffile(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit);   /* ref :19 */
+int32_t ezgdef_ffile_(int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, int32_t *iunit,
+                      F2Cl lengrtyp);                                              /* ref :17 */
+int32_t c_ezb200_set_fst_hooks(void *c_fstinf, void *c_fstsui, void *c_fstprm, void *c_fstluk);
 int32_t ezqkdef_(int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, int32_t *iunit,
                  F2Cl lengrtyp);                                                   /* ref :64 */
 int32_t c_ezgdef_supergrid(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t vercode, int32_t nsubgrids, int32_t *subgrid);

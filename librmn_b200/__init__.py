@@ -149,6 +149,11 @@ class EzLib:
         rc = self.lib.c_ezgxprm(gdid, C.byref(ni), C.byref(nj), t, *[C.byref(x) for x in ig], r, *[C.byref(x) for x in igr])
         return rc, ni.value, nj.value, t.value[:1].decode(), tuple(x.value for x in ig), r.value[:1].decode(), tuple(x.value for x in igr)
 
+    def gdgaxes(self, gdid, ax, ay):
+        _check_f32(ax, ay)
+        self.lib.c_gdgaxes.argtypes = [_i32, C.c_void_p, C.c_void_p]
+        return self.lib.c_gdgaxes(gdid, _ptr(ax), _ptr(ay))
+
     def ezget_nsubgrids(self, gdid):
         return self.lib.c_ezget_nsubgrids(gdid)
 

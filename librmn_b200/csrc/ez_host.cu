@@ -8,6 +8,7 @@
 // points exist, a tiny per-field pre-pass.  There is no CPU fallback: if no CUDA device is usable the
 // compute entry points print the CUDA error and return -1.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <ctype.h>
 #include <math.h>
 #include <stdint.h>
@@ -487,7 +488,10 @@ int add_grid(std::unique_ptr<Grid> g) {
     return g_grids.back()->id;
 }
 
-int gdef_fmem(int ni, int nj, const char *grtyp, const char *grref, int ig1, int ig2, int ig3, int ig4, const float *ax, const float *ay) {
+// keys: what c_ezgprm reports as ig1..ig4 when it differs from the reference grid's descriptors -- the ip1, ip2, ip3 (and the '#'
+// window origin) of the positional records a file-backed definition was read from (ez_lireEnrPositionnels.c:289-316)
+int gdef_fmem(int ni, int nj, const char *grtyp, const char *grref, int ig1, int ig2, int ig3, int ig4, const float *ax, const float *ay,
+              const int *keys = nullptr) {
     Lock lk;
     const char t = grtyp[0];
     const int ig[4] = {ig1, ig2, ig3, ig4};
@@ -503,7 +507,7 @@ int gdef_fmem(int ni, int nj, const char *grtyp, const char *grref, int ig1, int
         }
         const char rr = grref ? grref[0] : ' ';
         // 'G' grids are matched on (ni,nj,ig) alone (ez_findgrid.c:53-57)
-        int found = find_grid(t, (t == 'G') ? 'L' : rr, ni, nj, ig, ig, ax, ay, t != 'G');
+        int found = find_grid(t, (t == 'G') ? 'L' : rr, ni, nj, keys ? keys : ig, ig, ax, ay, t != 'G');
         if (found >= 0) {
             g_grids[found]->access_count++;
             return found;
@@ -513,7 +517,7 @@ int gdef_fmem(int ni, int nj, const char *grtyp, const char *grref, int ig1, int
         g->grref = rr;
         g->ni = ni;
         g->nj = nj;
-        for (int k = 0; k < 4; k++) { g->ig[k] = ig[k]; g->igref[k] = ig[k]; }
+        for (int k = 0; k < 4; k++) { g->ig[k] = keys ? keys[k] : ig[k]; g->igref[k] = ig[k]; }
         g->i1 = 1; g->i2 = ni; g->j1 = 1; g->j2 = nj;
         defxg(*g);
         if (defaxes(*g, ax, ay) < 0) return -1;
@@ -2168,16 +2172,164 @@ int32_t c_gdxpncf(int32_t gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *
 }
 int32_t gdxpncf_(int32_t *gdin, int32_t *i1, int32_t *i2, int32_t *j1, int32_t *j2) { return c_gdxpncf(*gdin, i1, i2, j1, j2); }
 
-int32_t c_ezqkdef(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit) {
-    (void)iunit;
-    char t = grtyp[0];
-    if (t == '#' || t == 'Y' || t == 'Z' || t == 'U' || t == ' ') {   // ezgdef_ffile.c:44-50
-        fprintf(stderr, "<c_ezqkdef> grid type '%c' needs positional records from an RPN standard file; FST I/O is outside the "
-                        "hot-path scope -- define it from memory with c_ezgdef_fmem / c_ezgdef_supergrid\n", t);
+// ---------------------------------------------------------------------------------------------------
+// N4: grids defined by positional records of an RPN standard file (ezgdef_ffile.c:29-140, ez_lireEnrPositionnels.c:12-349)
+// ---------------------------------------------------------------------------------------------------
+// The records are read through the caller's own FST layer: a drop-in replacement of the interpolator lives next to the librmn
+// that opened the file, so c_fstinf / c_fstsui / c_fstprm / c_fstluk are looked up in the process at the first
+// file-backed definition (dlsym), or handed over with c_ezb200_set_fst_hooks.  This library contains no file format code.
+typedef int (*fstinf_fn)(int iun, int *ni, int *nj, int *nk, int datev, const char *etiket, int ip1, int ip2, int ip3, const char *typvar,
+                         const char *nomvar);
+typedef int (*fstsui_fn)(int iun, int *ni, int *nj, int *nk);
+typedef int (*fstprm_fn)(int handle, int *dateo, int *deet, int *npas, int *ni, int *nj, int *nk, int *nbits, int *datyp, int *ip1, int *ip2,
+                         int *ip3, char *typvar, char *nomvar, char *etiket, char *grtyp, int *ig1, int *ig2, int *ig3, int *ig4, int *swa,
+                         int *lng, int *dltf, int *ubc, int *extra1, int *extra2, int *extra3);
+typedef int (*fstluk_fn)(void *field, int handle, int *ni, int *nj, int *nk);
+static struct { fstinf_fn inf; fstsui_fn sui; fstprm_fn prm; fstluk_fn luk; } g_fst = {nullptr, nullptr, nullptr, nullptr};
+
+static bool fst_ready() {
+    if (g_fst.inf && g_fst.sui && g_fst.prm && g_fst.luk) return true;
+    fstinf_fn a = (fstinf_fn)dlsym(RTLD_DEFAULT, "c_fstinf");
+    fstsui_fn b = (fstsui_fn)dlsym(RTLD_DEFAULT, "c_fstsui");
+    fstprm_fn c = (fstprm_fn)dlsym(RTLD_DEFAULT, "c_fstprm");
+    fstluk_fn d = (fstluk_fn)dlsym(RTLD_DEFAULT, "c_fstluk");
+    if (a && b && c && d) { g_fst.inf = a; g_fst.sui = b; g_fst.prm = c; g_fst.luk = d; return true; }
+    return false;
+}
+int32_t c_ezb200_set_fst_hooks(void *fstinf, void *fstsui, void *fstprm, void *fstluk) {
+    Lock lk;
+    g_fst.inf = (fstinf_fn)fstinf; g_fst.sui = (fstsui_fn)fstsui; g_fst.prm = (fstprm_fn)fstprm; g_fst.luk = (fstluk_fn)fstluk;
+    return (g_fst.inf && g_fst.sui && g_fst.prm && g_fst.luk) ? 0 : -1;
+}
+
+struct FstRec { int key, ni, nj, nk, ip1, ip2, ip3, ig[4]; char grtyp; };
+static int fst_prm(int key, FstRec &r) {
+    int dateo, deet, npas, nbits, bidon, swa, lng, dltf, ubc, e1, e2, e3;
+    char typvar[8] = "  ", nomvar[8] = "    ", etiket[16] = "            ", grtyp[4] = " ";
+    r.key = key;
+    const int ier = g_fst.prm(key, &dateo, &deet, &npas, &r.ni, &r.nj, &r.nk, &nbits, &bidon, &r.ip1, &r.ip2, &r.ip3, typvar, nomvar, etiket, grtyp,
+                              &r.ig[0], &r.ig[1], &r.ig[2], &r.ig[3], &swa, &lng, &dltf, &ubc, &e1, &e2, &e3);
+    r.grtyp = grtyp[0];
+    return ier;
+}
+
+// Lire_enrUvercode1, ez_lireEnrPositionnels.c:12-46: the '^>' record of a Yin-Yang grid
+static int gdef_u_record(const float *yy, int nix, const int keys[4]) {
+    if (nix < 16) return -1;
+    const int ndiv = (int)yy[2], ni = (int)yy[5], nj = (int)yy[6];
+    if (ndiv != 2 || ni <= 0 || nj <= 0 || nix < 2 * (15 + ni + nj) - 5) {
+        fprintf(stderr, "<LireEnrPositionnels>: malformed ^> record (ndiv %d, ni %d, nj %d, length %d)\n", ndiv, ni, nj, nix);
         return -1;
     }
+    const int yinsize = 15 + ni + nj;
+    std::vector<float> ax(yy + 15, yy + 15 + ni), ay(yy + 15 + ni, yy + 15 + ni + nj);
+    char z[2] = {'Z', 0}, e[2] = {'E', 0}, u[2] = {'U', 0}, f[2] = {'F', 0};
+    int sub[2];
+    for (int k = 0; k < 2; k++) {
+        const float *rot = k ? yy + yinsize + 6 : yy + 11;
+        float xg[4] = {rot[0], rot[1], rot[2], rot[3]};
+        int ig[4];
+        ezh::cxgaig('E', ig, xg);
+        sub[k] = gdef_fmem(ni, nj, z, e, ig[0], ig[1], ig[2], ig[3], ax.data(), ay.data());
+        if (sub[k] < 0) return -1;
+    }
+    const int gd = c_ezgdef_supergrid(ni, nj * ndiv, u, f, 1, 2, sub);
+    if (gd >= 0 && keys) {
+        Lock lk;
+        Grid *g = grid_of(gd);
+        if (g) for (int k = 0; k < 4; k++) g->ig[k] = keys[k];
+    }
+    return gd;
+}
+
+// c_ezgdef_ffile + LireEnrPositionnels for '#', 'Y', 'Z', 'U' and ' '
+static int gdef_ffile(int ni, int nj, char t, int ig1, int ig2, int ig3, int ig4, int iunit) {
+    if (!fst_ready()) {
+        fprintf(stderr, "<c_ezgdef_ffile> grid type '%c' needs positional records from an RPN standard file, and this process exports no "
+                        "c_fstinf / c_fstsui / c_fstprm / c_fstluk (link the librmn that opened unit %d, or call c_ezb200_set_fst_hooks)\n", t, iunit);
+        return -1;
+    }
+    const char blank12[] = "            ", blank2[] = "  ";
+    int n1, n2, n3;
+    if (t == 'U') {
+        int key = g_fst.inf(iunit, &n1, &n2, &n3, -1, blank12, ig1, ig2, ig3, blank2, "^>  ");
+        FstRec r;
+        bool found = false;
+        while (!found && key > 0) {
+            const int ier = fst_prm(key, r);
+            if (r.ni > 0 && r.nj == 1 && ier >= 0) found = true;
+            else key = g_fst.sui(iunit, &n1, &n2, &n3);
+        }
+        if (!found) { fprintf(stderr, "<LireEnrPositionnels>: Positional records ^> not found. Exiting...\n\n"); return -1; }
+        if (r.grtyp != 'F') { fprintf(stderr, "<LireEnrPositionnels>: Unknown reference grid %c for grid type U. Exiting...\n", r.grtyp); return -1; }
+        if (r.ig[0] != 1) { fprintf(stderr, "<LireEnrPositionnels>: ^> record with vercode %d: only vercode 1 is defined\n", r.ig[0]); return -1; }
+        std::vector<float> yy((size_t)r.ni);
+        if (g_fst.luk(yy.data(), r.key, &n1, &n2, &n3) < 0) return -1;
+        const int keys[4] = {r.ip1, r.ip2, r.ip3, ig4};
+        return gdef_u_record(yy.data(), r.ni, keys);
+    }
+    const int tmpip3 = (t == '#') ? -1 : ig3;
+    // '>>'
+    FstRec rx, ry;
+    int key = g_fst.inf(iunit, &n1, &n2, &n3, -1, blank12, ig1, ig2, tmpip3, blank2, ">>  ");
+    if ((ni == 0 || ni == -1) && key > 0) ni = n1;
+    bool fx = false, fy = false;
+    while (!fx && key > 0) {
+        fst_prm(key, rx);
+        if (rx.ni == ni || t == '#') fx = true;
+        else key = g_fst.sui(iunit, &n1, &n2, &n3);
+    }
+    // '^^'
+    key = g_fst.inf(iunit, &n1, &n2, &n3, -1, blank12, ig1, ig2, tmpip3, blank2, "^^  ");
+    if ((nj == 0 || nj == -1) && key > 0) nj = n2;
+    while (!fy && key > 0) {
+        fst_prm(key, ry);
+        if (ry.nj == nj || t == '#') fy = true;
+        else key = g_fst.sui(iunit, &n1, &n2, &n3);
+    }
+    if (!fx || !fy) { fprintf(stderr, "<LireEnrPositionnels>: Positional records ^^ and >> not found. Exiting...\n\n"); return -1; }
+    char gt = t;
+    if (ry.ni == rx.ni && ry.nj == rx.nj) gt = 'Y';
+    else if (t != '#') gt = 'Z';
+    const char grref = ry.grtyp;   // (the check looks at the '^^' record's reference, the descriptors kept are the '>>' record's)
+    if (grref != 'N' && grref != 'S' && grref != 'L' && grref != 'E' && grref != 'O') {
+        fprintf(stderr, "<LireEnrPositionnels>: Unknown reference grid. Exiting...\n");
+        return -1;
+    }
+    std::vector<float> ay((size_t)ry.ni * ry.nj), ax((size_t)rx.ni * rx.nj);
+    if (g_fst.luk(ay.data(), ry.key, &n1, &n2, &n3) < 0 || g_fst.luk(ax.data(), rx.key, &n1, &n2, &n3) < 0) return -1;
+    std::vector<float> gax, gay;
+    if (gt == '#') {   // Lire_enrTicTac: the (ig3, ig4) window of the full axes
+        if (ig3 < 1 || ig4 < 1 || (size_t)(ig3 - 1 + ni) > ax.size() || (size_t)(ig4 - 1 + nj) > ay.size()) {
+            fprintf(stderr, "<LireEnrPositionnels>: '#' window (%d, %d) + %d x %d leaves the positional records\n", ig3, ig4, ni, nj);
+            return -1;
+        }
+        gax.assign(ax.begin() + (ig3 - 1), ax.begin() + (ig3 - 1) + ni);
+        gay.assign(ay.begin() + (ig4 - 1), ay.begin() + (ig4 - 1) + nj);
+    } else {
+        gax = ax; gay = ay;
+    }
+    if (grref == 'L')
+        for (int i = 0; i < ni && i < (int)gax.size(); i++)
+            if (gax[i] < 0.0f) gax[i] += 360.0f;
+    const int keys[4] = {rx.ip1, rx.ip2, gt == '#' ? ig3 : rx.ip3, gt == '#' ? ig4 : 0};
+    char tt[2] = {gt, 0}, rr[2] = {grref, 0};
+    return gdef_fmem(ni, nj, tt, rr, rx.ig[0], rx.ig[1], rx.ig[2], rx.ig[3], gax.data(), gay.data(), keys);
+}
+int32_t c_ezgdef_ffile(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit) {
+    const char t = grtyp[0];
+    if (t == '#' || t == 'Y' || t == 'Z' || t == 'U' || t == ' ') return gdef_ffile(ni, nj, t, ig1, ig2, ig3, ig4, iunit);   // ezgdef_ffile.c:44-50
     char r[2] = {' ', 0};
     return c_ezgdef_fmem(ni, nj, grtyp, r, ig1, ig2, ig3, ig4, nullptr, nullptr);
+}
+int32_t ezgdef_ffile_(int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, int32_t *iunit, F2Cl l) {
+    (void)l;
+    char t[2] = {grtyp[0], 0};
+    return c_ezgdef_ffile(*ni, *nj, t, *ig1, *ig2, *ig3, *ig4, *iunit);
+}
+// ezqkdef.c: c_ezqkdef is c_ezgdef_ffile
+int32_t c_ezqkdef(int32_t ni, int32_t nj, char *grtyp, int32_t ig1, int32_t ig2, int32_t ig3, int32_t ig4, int32_t iunit) {
+    return c_ezgdef_ffile(ni, nj, grtyp, ig1, ig2, ig3, ig4, iunit);
 }
 int32_t ezqkdef_(int32_t *ni, int32_t *nj, char *grtyp, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, int32_t *iunit, F2Cl l) {
     (void)l;
@@ -2189,10 +2341,8 @@ int32_t c_ezgdef(int32_t ni, int32_t nj, char *grtyp, char *grref, int32_t ig1, 
         fprintf(stderr, "The '#' grid type is not supported with ezgdef.\nPlease use ezgdef_ffile or ezgdef_fmem\n");
         return -1;
     }
-    if ((grtyp[0] == 'Y' || grtyp[0] == 'Z') && grref && (0 == strcmp(grref, "FILE") || 0 == strcmp(grref, "file"))) {
-        fprintf(stderr, "<c_ezgdef> FILE sources need FST I/O, which is outside the hot-path scope\n");
-        return -1;
-    }
+    if ((grtyp[0] == 'Y' || grtyp[0] == 'Z') && grref && (0 == strcmp(grref, "FILE") || 0 == strcmp(grref, "file")))
+        return c_ezgdef_ffile(ni, nj, grtyp, ig1, ig2, ig3, ig4, ig4);   // ezgdef.c:59-90 (the unit travels in ig4)
     return c_ezgdef_fmem(ni, nj, grtyp, grref, ig1, ig2, ig3, ig4, ax, ay);
 }
 int32_t ezgdef_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *ig1, int32_t *ig2, int32_t *ig3, int32_t *ig4, float *ax, float *ay,

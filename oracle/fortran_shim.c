@@ -1728,8 +1728,41 @@ void lorenzo_mask_fill_(float *fld, fint *masque, fint *pni, fint *pnj, fint *me
 #undef MSK
 }
 void qqq_ezget_mask_zones_(void) { off_path("qqq_ezget_mask_zones"); }
-int fstluk_(void) { off_path("fstluk"); return -1; }
-int fstprm_(void) { off_path("fstprm"); return -1; }
-int c_fstinf(void) { off_path("c_fstinf"); return -1; }
-int c_fstprm(void) { off_path("c_fstprm"); return -1; }
-int c_fstsui(void) { off_path("c_fstsui"); return -1; }
+/* FST access of ez_lireEnrPositionnels.c (c_fstinf / c_fstsui / c_fstprm, f77 fstluk / fstprm): the reference's file layer
+ * (src/fstd98) is not part of the oracle; tests hand in an in-memory record table through oracle_set_fst_hooks (same C
+ * signatures as rmn/fstd98.h:42-67) so that the reference's own grid-definition code can be run against it. */
+typedef int (*o_fstinf_fn)(int, int *, int *, int *, int, const char *, int, int, int, const char *, const char *);
+typedef int (*o_fstsui_fn)(int, int *, int *, int *);
+typedef int (*o_fstprm_fn)(int, int *, int *, int *, int *, int *, int *, int *, int *, int *, int *, int *, char *, char *, char *, char *, int *, int *,
+                           int *, int *, int *, int *, int *, int *, int *, int *, int *);
+typedef int (*o_fstluk_fn)(void *, int, int *, int *, int *);
+static o_fstinf_fn h_fstinf; static o_fstsui_fn h_fstsui; static o_fstprm_fn h_fstprm; static o_fstluk_fn h_fstluk;
+void oracle_set_fst_hooks(void *inf, void *sui, void *prm, void *luk) {
+    h_fstinf = (o_fstinf_fn)inf; h_fstsui = (o_fstsui_fn)sui; h_fstprm = (o_fstprm_fn)prm; h_fstluk = (o_fstluk_fn)luk;
+}
+int c_fstinf(int iun, int *ni, int *nj, int *nk, int datev, const char *etiket, int ip1, int ip2, int ip3, const char *typvar, const char *nomvar) {
+    if (!h_fstinf) { off_path("c_fstinf"); return -1; }
+    return h_fstinf(iun, ni, nj, nk, datev, etiket, ip1, ip2, ip3, typvar, nomvar);
+}
+int c_fstsui(int iun, int *ni, int *nj, int *nk) {
+    if (!h_fstsui) { off_path("c_fstsui"); return -1; }
+    return h_fstsui(iun, ni, nj, nk);
+}
+int c_fstprm(int handle, int *dateo, int *deet, int *npas, int *ni, int *nj, int *nk, int *nbits, int *datyp, int *ip1, int *ip2, int *ip3,
+             char *typvar, char *nomvar, char *etiket, char *grtyp, int *ig1, int *ig2, int *ig3, int *ig4, int *swa, int *lng, int *dltf,
+             int *ubc, int *extra1, int *extra2, int *extra3) {
+    if (!h_fstprm) { off_path("c_fstprm"); return -1; }
+    return h_fstprm(handle, dateo, deet, npas, ni, nj, nk, nbits, datyp, ip1, ip2, ip3, typvar, nomvar, etiket, grtyp, ig1, ig2, ig3, ig4, swa,
+                    lng, dltf, ubc, extra1, extra2, extra3);
+}
+int fstprm_(int *handle, int *dateo, int *deet, int *npas, int *ni, int *nj, int *nk, int *nbits, int *datyp, int *ip1, int *ip2, int *ip3,
+            char *typvar, char *nomvar, char *etiket, char *grtyp, int *ig1, int *ig2, int *ig3, int *ig4, int *swa, int *lng, int *dltf,
+            int *ubc, int *extra1, int *extra2, int *extra3, F2Cl l1, F2Cl l2, F2Cl l3, F2Cl l4) {
+    (void)l1; (void)l2; (void)l3; (void)l4;
+    return c_fstprm(*handle, dateo, deet, npas, ni, nj, nk, nbits, datyp, ip1, ip2, ip3, typvar, nomvar, etiket, grtyp, ig1, ig2, ig3, ig4, swa,
+                    lng, dltf, ubc, extra1, extra2, extra3);
+}
+int fstluk_(void *field, int *handle, int *ni, int *nj, int *nk) {
+    if (!h_fstluk) { off_path("fstluk"); return -1; }
+    return h_fstluk(field, *handle, ni, nj, nk);
+}
