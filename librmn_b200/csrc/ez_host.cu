@@ -2388,7 +2388,10 @@ int32_t c_ezgdef_supergrid(int32_t ni, int32_t nj, char *grtyp, char *grref, int
     g->subgrid[1] = subgrid[1];
     g->i1 = 1; g->i2 = ni; g->j1 = 1; g->j2 = nj;
     int id = add_grid(std::move(g));
-    for (int k = 0; k < 2; k++) gdef_yymask(*grid_of(subgrid[k]));
+    for (int k = 0; k < 2; k++) {
+        gdef_yymask(*grid_of(subgrid[k]));
+        grid_of(subgrid[k])->access_count++;   // the supergrid holds its sub-grids: c_gdrls on them alone cannot pull them from under it
+    }
     return id;
 }
 int32_t ezgdef_supergrid_(int32_t *ni, int32_t *nj, char *grtyp, char *grref, int32_t *vercode, int32_t *nsubgrids, int32_t *subgrid, F2Cl l1,
@@ -2418,6 +2421,10 @@ int32_t c_gdrls(int32_t gdin) {   // gdrls.c:34-90
             d.ready = false;
         }
         g->alive = false;
+        // what the grid held: the sub-grids of a supergrid, the mask grid of a Yin / Yang panel
+        for (int k = 0; k < g->nsubgrids && k < 2; k++)
+            if (g->subgrid[k] >= 0) c_gdrls(g->subgrid[k]);
+        if (g->mymaskgrid >= 0) { const int m = g->mymaskgrid; g->mymaskgrid = -1; c_gdrls(m); }
     }
     return 0;
 }
