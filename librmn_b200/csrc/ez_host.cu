@@ -87,6 +87,12 @@ struct Gset {   // _gridset, ez_def.h:148-166, device-resident
     int *d_zlist[2] = {nullptr, nullptr};
     int nzlist[2] = {0, 0};
     bool zlist_built[2] = {false, false};
+    // direct kernel, cubic on an irregular source: per-point plans (k_plan_cache), built at the second direct call on the gridset
+    int *d_dc_idx = nullptr;
+    float4 *d_dc_wx = nullptr, *d_dc_wy = nullptr;
+    float *d_dc_sm1 = nullptr;
+    bool dc_tried = false;
+    int dc_calls = 0;
     int counts[6] = {0, 0, 0, 0, 0, 0};   // DEHORS, AU_NORD, AU_SUD, POLE_NORD, POLE_SUD, yang
     // 'Y' cloud SOURCE (ez_cloud.cu; the reference's _ygrid, ez_def.h:136-146): k nearest source points and weights per target point
     bool cloud = false;
@@ -166,9 +172,15 @@ struct Unlocked {   // releases every level this thread holds for the duration o
 };
 std::vector<std::unique_ptr<Grid>> g_grids;
 
+// Per-thread device resources are released when a caller's worker thread ends (the CUDA runtime is alive then).  The main
+// thread's are left to process teardown: its thread_local destructors run inside exit(), when the runtime may be gone.
+static const std::thread::id g_main_thread = std::this_thread::get_id();
+inline bool thread_may_release() { return std::this_thread::get_id() != g_main_thread; }
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    ~DevBuf() { if (p && thread_may_release()) { cudaFree(p); (void)cudaGetLastError(); } }
     void *get(size_t bytes) {
         if (bytes > cap) {
             if (p) cudaFree(p);
@@ -216,6 +228,15 @@ struct Session {   // the reference's __thread statics (ez_statics.c:12-17) plus
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     DevBuf st_pts[10];          // staging of caller arrays in the scattered-point API
     DevBuf prow[2];             // synthetic pole rows of (u, v) for the polar vector correction (K18)
+    ~Session() {
+        if (!thread_may_release()) return;
+        cudaStream_t streams[] = {own_stream, s_h2d, s_d2h, fork.aux[0], fork.aux[1]};
+        for (cudaStream_t st : streams) if (st) cudaStreamDestroy(st);
+        cudaEvent_t events[] = {tev.ev[0], tev.ev[1], tev.ev[2], tev.ev[3], fork.ev_fork, fork.ev_join[0], fork.ev_join[1],
+                                ev_in[0], ev_in[1], ev_comp[0], ev_comp[1], ev_out[0], ev_out[1]};
+        for (cudaEvent_t e : events) if (e) cudaEventDestroy(e);
+        (void)cudaGetLastError();
+    }
 };
 thread_local Session S;
 
@@ -952,6 +973,8 @@ void free_gset(Gset &gs) {
     gs.d_wrot = nullptr; gs.wrot_tried = false;
     gs.d_perm = nullptr; gs.perm_tried = false;
     for (int k = 0; k < 2; k++) { gs.d_zlist[k] = nullptr; gs.nzlist[k] = 0; gs.zlist_built[k] = false; }
+    cudaFree(gs.d_dc_idx); cudaFree(gs.d_dc_wx); cudaFree(gs.d_dc_wy); cudaFree(gs.d_dc_sm1);
+    gs.d_dc_idx = nullptr; gs.d_dc_wx = gs.d_dc_wy = nullptr; gs.d_dc_sm1 = nullptr; gs.dc_tried = false; gs.dc_calls = 0;
     gs.d_x = gs.d_y = nullptr;
     gs.d_zb = nullptr;
     gs.built = false;
@@ -1234,6 +1257,28 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
             a.zout = zo;
         }
         a.wrot = (wrot && nfields == 2) ? wrot : nullptr;
+        // cubic on an irregular source: from the second call on, the per-point plans come from a cache (bit-identical weights)
+        if (a.o.degree == EZ_CUBIC && (a.yy || in.grtyp == 'Z' || in.grtyp == '#' || in.grtyp == 'G') && a.src.ni < 65536 &&
+            (a.src.j2 - a.src.j1 + 1) < 32768 && (!a.yy || (a.src2.ni < 65536 && (a.src2.j2 - a.src2.j1 + 1) < 32768))) {
+            static const bool dc_on = !(getenv("EZB200_DIRECT_PLAN_CACHE") && atoi(getenv("EZB200_DIRECT_PLAN_CACHE")) == 0);
+            if (dc_on && !gs->dc_tried && ++gs->dc_calls >= 2) {
+                gs->dc_tried = true;
+                const size_t n = (size_t)a.npts;
+                if (cudaMalloc((void **)&gs->d_dc_idx, n * sizeof(int)) == cudaSuccess && cudaMalloc((void **)&gs->d_dc_wx, n * sizeof(float4)) == cudaSuccess &&
+                    cudaMalloc((void **)&gs->d_dc_wy, n * sizeof(float4)) == cudaSuccess && cudaMalloc((void **)&gs->d_dc_sm1, n * sizeof(float)) == cudaSuccess) {
+                    InterpArgs pa = a;
+                    pa.band_j0 = pa.band_j1 = 0;
+                    ezk::plan_cache(pa, gs->d_dc_idx, gs->d_dc_wx, gs->d_dc_wy, gs->d_dc_sm1, S.stream, 1);
+                    S.launches++;
+                    (void)cudaStreamSynchronize(S.stream);   // shared by every session: complete before other streams may read it
+                } else {
+                    (void)cudaGetLastError();
+                    cudaFree(gs->d_dc_idx); cudaFree(gs->d_dc_wx); cudaFree(gs->d_dc_wy); cudaFree(gs->d_dc_sm1);
+                    gs->d_dc_idx = nullptr; gs->d_dc_wx = gs->d_dc_wy = nullptr; gs->d_dc_sm1 = nullptr;
+                }
+            }
+            if (gs->d_dc_idx) { a.pc_idx = gs->d_dc_idx; a.pc_wx = gs->d_dc_wx; a.pc_wy = gs->d_dc_wy; a.pc_sm1 = gs->d_dc_sm1; }
+        }
         const bool timed_direct = S.timing && S.tev.ev[0];
         S.launches += ezk::interp_direct(a, zl, nz, S.stream, ensure_fork() ? &S.fork : nullptr, &pre, timed_direct ? &S.tev : nullptr);
         if (a.wrot) {
@@ -1532,6 +1577,7 @@ CopyPool &g_copy_pool = *new CopyPool;
 struct PinBuf {   // pinned host ring slot
     void *p = nullptr;
     size_t cap = 0;
+    ~PinBuf() { if (p && thread_may_release()) { cudaFreeHost(p); (void)cudaGetLastError(); } }
     void *get(size_t bytes) {
         if (bytes > cap) {
             if (p) cudaFreeHost(p);
@@ -1944,7 +1990,11 @@ int uvint_dev(Grid &out, Grid &in, float *d_uo, float *d_vo, const float *d_ui, 
         }
         const long uv_in = (long)(vi - ui), uv_out = (long)(d_vo - d_uo);
         const bool uv_near = (uv_in < 0 ? -uv_in : uv_in) < (1L << 26) && (uv_out < 0 ? -uv_out : uv_out) < (1L << 40);
-        if (nfields == 1 && !prow_u && !prow_v && !eff_in->needs_expansion && uv_near) {
+        // (the tile kernels address a stage through 32-bit offsets, hence uv_near; the direct kernel, which takes a pair unless it
+        //  is switched off, has no such limit -- callers' u and v arrays may lie anywhere)
+        const bool direct_likely = (S.call_fields > 0 ? S.call_fields : 2) <= S.direct_max && S.direct_max >= 2 && S.arith == 2 &&
+                                   (S.opt.degre_interp == EZ_LINEAR || S.opt.degre_interp == EZ_CUBIC) && out.grtyp != 'Y';
+        if (nfields == 1 && !prow_u && !prow_v && !eff_in->needs_expansion && (uv_near || direct_likely)) {
             // one (u, v) pair, no synthetic pole rows, no hemispheric mirror (the only place the two components are treated
             // differently): ONE launch over two "fields" whose stride is the distance between the caller's arrays, so the
             // gridset, the plans and the tile setup are read and built once for both components

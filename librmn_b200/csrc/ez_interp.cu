@@ -883,10 +883,10 @@ void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned i
     k_tile_list<<<grid, TT * TT, 0, s>>>(a, flags, list, cursor, mode);
 }
 
-void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s) {
+void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s, int mark_split) {
     const int nb = (a.npts + 255) / 256;
-    if (a.o.degree == EZ_CUBIC) k_plan_cache<3><<<nb, 256, 0, s>>>(a, idx, wx, wy, sm1);
-    else k_plan_cache<1><<<nb, 256, 0, s>>>(a, idx, wx, wy, sm1);
+    if (a.o.degree == EZ_CUBIC) k_plan_cache<3><<<nb, 256, 0, s>>>(a, idx, wx, wy, sm1, mark_split);
+    else k_plan_cache<1><<<nb, 256, 0, s>>>(a, idx, wx, wy, sm1, mark_split);
 }
 
 int interp(const InterpArgs &a, cudaStream_t s, const InterpTiming *timing, const InterpFork *fork) {

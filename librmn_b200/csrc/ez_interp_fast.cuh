@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(TPB) k_interp_fast(const __grid_constant__ Int
 template <int DEG>
 __device__ __forceinline__ void direct_body(const GridDev &g, const InterpArgs &a, const float *__restrict__ z, int n, float px, float py) {
     const long is = a.in_stride, os = a.out_stride;
+    const int nf = a.nfields;
     float *zo = a.zout + n;
     if (DEG == 1) {
         const PlanLinF p = to_f32(plan_linear(g, px, py));
@@ -442,9 +443,24 @@ __device__ __forceinline__ void direct_body(const GridDev &g, const InterpArgs &
             zo[os] = fmaf(r.w, v, r.z * u);
             return;
         }
-        for (int f = 0; f < a.nfields; f++) zo[f * os] = eval_linear_f32(p, z + f * is);
+        for (int f = 0; f < nf; f++) zo[f * os] = eval_linear_f32(p, z + f * is);
     } else {
-        const PlanCubF p = to_f32(plan_cubic(g, px, py));
+        // irregular sources, from the second call on a gridset: the plan comes from the gridset's cache (40 B per point,
+        // k_plan_cache: the same fp32 weights to the bit) instead of ~30 fp32 <-> fp64 conversions and the fp64 Newton arithmetic
+        PlanCubF p;
+        int k = -1;
+        if (a.pc_idx) k = __ldg(a.pc_idx + n);
+        if (k >= 0) {
+            const int c0 = k & 0xffff;
+            const float4 X = __ldg(a.pc_wx + n), Y = __ldg(a.pc_wy + n);
+            p.c[0] = c0; p.c[1] = c0 + 1; p.c[2] = c0 + 2; p.c[3] = c0 + 3;
+            p.ni = g.ni; p.r0 = (k >> 16) * g.ni;
+            p.wx[0] = X.x; p.wx[1] = X.y; p.wx[2] = X.z; p.wx[3] = X.w;
+            p.wy[0] = Y.x; p.wy[1] = Y.y; p.wy[2] = Y.z; p.wy[3] = Y.w;
+            p.sm1 = __ldg(a.pc_sm1 + n);
+        } else {
+            p = to_f32(plan_cubic(g, px, py));
+        }
         if (a.wrot) {
             const float u = eval_cubic_f32(p, z), v = eval_cubic_f32(p, z + is);
             const float4 r = __ldg(a.wrot + n);
@@ -452,7 +468,7 @@ __device__ __forceinline__ void direct_body(const GridDev &g, const InterpArgs &
             zo[os] = fmaf(r.w, v, r.z * u);
             return;
         }
-        for (int f = 0; f < a.nfields; f++) zo[f * os] = eval_cubic_f32(p, z + f * is);
+        for (int f = 0; f < nf; f++) zo[f * os] = eval_cubic_f32(p, z + f * is);
     }
 }
 

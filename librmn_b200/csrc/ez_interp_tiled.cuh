@@ -315,16 +315,20 @@ __global__ void __launch_bounds__(256) k_store_const(const __grid_constant__ Int
 }
 
 // third pass: the plan of every target point, stored for the tile kernels (40 B per point)
+// mark_split: a point whose stencil columns are not contiguous (the longitudinal seam) gets idx = -1 -- the direct kernel, which
+// has no classification to keep such points away from the cache, then evaluates its plan on the fly
 template <int DEG>
 __global__ void __launch_bounds__(256) k_plan_cache(const __grid_constant__ InterpArgs a, int *__restrict__ idx, float4 *__restrict__ wxo,
-                                                    float4 *__restrict__ wyo, float *__restrict__ sm1o) {
+                                                    float4 *__restrict__ wyo, float *__restrict__ sm1o, int mark_split) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= a.npts) return;
     const uint8_t bits = a.zb ? a.zb[n] : (uint8_t)0;
     int c0 = 0, r0 = 0;
     float wx[4] = {0.f, 0.f, 0.f, 0.f}, wy[4] = {0.f, 0.f, 0.f, 0.f}, s = 0.f;
-    if (a.yy && (bits & ZB_YANG)) point_plan<DEG>(a.src2, a.x[n], a.y[n], c0, r0, wx, wy, s);
-    else point_plan<DEG>(a.src, a.x[n], a.y[n], c0, r0, wx, wy, s);
+    bool ok;
+    if (a.yy && (bits & ZB_YANG)) ok = point_plan<DEG>(a.src2, a.x[n], a.y[n], c0, r0, wx, wy, s);
+    else ok = point_plan<DEG>(a.src, a.x[n], a.y[n], c0, r0, wx, wy, s);
+    if (mark_split && !ok) { idx[n] = -1; return; }
     idx[n] = (r0 << 16) | (c0 & 0xffff);
     wxo[n] = make_float4(wx[0], wx[1], wx[2], wx[3]);
     wyo[n] = make_float4(wy[0], wy[1], wy[2], wy[3]);

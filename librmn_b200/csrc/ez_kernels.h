@@ -129,7 +129,7 @@ bool tiled_eligible(const InterpArgs &a);
 void tile_dims(int out_ni, int out_nj, int *ntx, int *nty);
 void tile_classify(const InterpArgs &a, TileDesc *tiles, uint32_t *flags, unsigned int *rowy, unsigned int *counters, cudaStream_t s);
 void tile_list(const InterpArgs &a, const uint32_t *flags, int *list, unsigned int *cursor, int mode, cudaStream_t s);
-void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s);
+void plan_cache(const InterpArgs &a, int *idx, float4 *wx, float4 *wy, float *sm1, cudaStream_t s, int mark_split = 0);
 // 'Y' point clouds as a SOURCE (ez_cloud.cu): k nearest source points + inverse-square-distance weights per target point
 // ([nw][ndst] plane-major, 1-based indices, 0 = empty slot), and their application to nfields fields
 bool cloud_build(const float *src_lat, const float *src_lon, int nsrc, const float *dst_lat, const float *dst_lon, int ndst, int nw,

@@ -7,8 +7,8 @@
 // MODE 0: FFMA only          (16 independent chains)
 // MODE 1: FFMA2 only         (8 independent chains of packed pairs)
 // MODE 2: FFMA2 + FFMA mixed (8 packed chains + 8 scalar chains, interleaved 1:1)
-// MODE 3: FFMA2 + LDS.32     (8 packed chains, one conflict-free LDS per 3 FFMA2, as in the window kernel: 50 LDS / 153 FMA-pipe)
-// MODE 4: LDS.32 only
+// (modes 3 / 4, FFMA2 beside LDS and LDS alone, are kept in the source but not run: the compiler drops loads whose value is not
+//  consumed, so their first version measured nothing -- see profiles/r2_ubench_pipes.txt for what WAS measured)
 // MODE 5: FFMA2 with a scalar broadcast weight (the window kernel's operand form) + FADD2
 template <int MODE>
 __global__ void __launch_bounds__(128) k(float *out, int iters, float a, float b) {
@@ -66,8 +66,6 @@ int main() {
         run<0>("FFMA", out, c, 64, 0);
         run<1>("FFMA2", out, c, 64, 0);
         run<2>("FFMA2 + FFMA 1:1", out, c, 96, 0);
-        run<3>("FFMA2 + LDS (3:1)", out, c, 64, 12);
-        run<4>("LDS + FADD", out, c, 32, 32);
         run<5>("FFMA2 bcast w + FADD2 (3:1)", out, c, 64, 0);
     }
     return 0;
