@@ -1,12 +1,18 @@
-"""After scripts/final_sweep.sh <tag> (run under gpurun): turn gpurun_out/<tag>_* into the tracked summaries under profiles/
-(ncu per-kernel text summaries, bench lines, launch list, sanitizer logs) and refresh profiles/traffic_c{1,2,3,5}.json from the
-ncu captures.    usage: python scripts/post_sweep.py <tag>"""
+"""Two steps around scripts/final_sweep.sh <tag>:
+  on the GPU box (called by the sweep itself):  python scripts/post_sweep.py <tag>
+      every gpurun_out/<tag>_*.ncu-rep -> gpurun_out/<tag>_ncu_*.txt (per-kernel summary) + gpurun_out/<tag>_traffic_*.json (DRAM bytes
+      per launch); the sweep then deletes the reports (gpurun brings back at most 64 MiB)
+  here, afterwards:                             python scripts/post_sweep.py <tag> --publish
+      gpurun_out/<tag>_*.{json,csv,txt} -> profiles/ ; <tag>_traffic_cN.json -> profiles/traffic_cN.json"""
 import csv, json, os, re, shutil, subprocess, sys
 T = sys.argv[1]
 G, P = "gpurun_out", "profiles"
-for f in sorted(os.listdir(G)):
-    if f.startswith(T + "_") and (f.endswith(".json") or f.endswith(".csv") or f.endswith(".txt")) and os.path.getsize(os.path.join(G, f)) > 0:
-        shutil.copy(os.path.join(G, f), os.path.join(P, f))
+if "--publish" in sys.argv:
+    for f in sorted(os.listdir(G)):
+        if f.startswith(T + "_") and (f.endswith(".json") or f.endswith(".csv") or f.endswith(".txt")) and os.path.getsize(os.path.join(G, f)) > 0:
+            m = re.match(re.escape(T) + r"_(traffic_c\d\.json)$", f)
+            shutil.copy(os.path.join(G, f), os.path.join(P, m.group(1) if m else f))
+    sys.exit(0)
 def raw(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -20,12 +26,7 @@ for rep, wl, lev, alg in (("c2_tilekernels", "c2", 80, 2888356240), ("c5_rowsep"
     if not os.path.exists(path):
         print("missing", path); continue
     txt = subprocess.run([sys.executable, "scripts/ncu_summary.py", path], capture_output=True, text=True).stdout
-    open(os.path.join(P, "%s_ncu_%s.txt" % (T, rep)), "w").write(txt)
-    ks = {}
-    for r in raw(path):
-        rd, wr = float(r["dram__bytes_read.sum"]), float(r["dram__bytes_write.sum"])
-        # units: ncu prints Mbyte / Gbyte per column; the raw page keeps one unit per column, given in row 1 -- re-read it
-        ks[short(r["Kernel Name"])] = (rd, wr)
+    open(os.path.join(G, "%s_ncu_%s.txt" % (T, rep)), "w").write(txt)
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h, u = rows[0], rows[1]
@@ -42,5 +43,5 @@ for rep, wl, lev, alg in (("c2_tilekernels", "c2", 80, 2888356240), ("c5_rowsep"
           "kernels": kern, "dram_bytes_per_launch": sum(k["dram_bytes_per_launch"] for k in kern.values())}
     if alg:
         tj["algorithmic_bytes_per_step"] = alg
-    json.dump(tj, open(os.path.join(P, "traffic_%s.json" % wl), "w"), indent=1)
+    json.dump(tj, open(os.path.join(G, "%s_traffic_%s.json" % (T, wl)), "w"), indent=1)
     print(wl, {k: "%.0f MB in %.1f us" % (v["dram_bytes_per_launch"] / 1e6, v["gpu_time_us"]) for k, v in kern.items()})
