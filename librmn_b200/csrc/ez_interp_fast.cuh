@@ -473,7 +473,7 @@ __device__ __forceinline__ void direct_body(const GridDev &g, const InterpArgs &
 }
 
 #ifndef EZ_DIRECT_MINB
-#define EZ_DIRECT_MINB 3
+#define EZ_DIRECT_MINB 4
 #endif
 #ifndef EZ_DIRECT_MINB_LIN
 #define EZ_DIRECT_MINB_LIN 4
