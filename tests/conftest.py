@@ -70,15 +70,40 @@ class StableOracle:
         return self._stable(self._lib.ezwdint, [spdout, wdout], (spdout, wdout, uuin, vvin))
 
 
-@pytest.fixture(scope="session")
+_oracle_tmp = []
+
+
+def _fresh_oracle_copy():
+    """A private copy of libezref.so: dlopen of a distinct file gives a distinct instance with pristine static state."""
+    import shutil
+    import tempfile
+    if not _oracle_tmp:
+        _oracle_tmp.append(tempfile.mkdtemp(prefix="ezref_"))
+    path = os.path.join(_oracle_tmp[0], "libezref_%d.so" % len(os.listdir(_oracle_tmp[0])))
+    shutil.copy(REF_SO, path)
+    return path
+
+
+@pytest.fixture
 def ezref():
+    """A FRESH instance of the oracle per test.  The reference keeps process-wide tables (grids, and per target grid a hash table of
+    gridsets that is re-allocated as it fills, ezdefset.c:168-224); every re-definition of a 'U' grid lands on a new grid id because
+    its identity CRC includes heap bytes past a sub-grid's axis (ezgdef_supergrid.c:82), so over a long pytest session the tables of
+    the commonly used target grids grow without bound, and late Yin-Yang cases now and then came back with rc = -1 or a field of
+    garbage from the reference.  One library instance per test keeps every table small."""
     from librmn_b200 import EzLib
     if not _ensure_oracle():
         pytest.skip("oracle/_ref/libezref.so is not built and /root/reference is not available to build it")
-    lib = StableOracle(EzLib(REF_SO))
+    lib = StableOracle(EzLib(_fresh_oracle_copy()))
     yield lib
     if lib.flakes:
         sys.stderr.write("<oracle> %d interpolation call(s) had to be arbitrated (non-deterministic reference)\n" % lib.flakes)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    import shutil
+    for d in _oracle_tmp:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 @pytest.fixture(scope="session")
