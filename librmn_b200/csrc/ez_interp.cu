@@ -724,6 +724,9 @@ __global__ void __launch_bounds__(TPB) k_avg(const __grid_constant__ InterpArgs 
     int istart = f_ifix(xl), iend = f_nint(xh);
     if ((0.5f + (float)istart) < xl) istart = istart + 1;
     if (j == 1 && (float)iend < xh) iend = iend + 1;
+    // sph_average on a target row at a pole: 1 / cos(lat) is ~1e7 of either sign and the cell "covers" 1e8 source columns; the
+    // reference reads far outside its work array there (undefined).  Bound the walk so that no thread loops for seconds.
+    if ((long)iend - (long)istart > 8L * ni_src) { istart = max(istart, 1 - 4 * ni_src); iend = min(iend, 5 * ni_src); }
     AvgSrc src;
     src.ni = ni_src; src.nj = nj_src; src.ext = a.src.ext;
     for (int f = 0; f < a.nfields; f++) {

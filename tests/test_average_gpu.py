@@ -27,6 +27,11 @@ def _pairs(lib):
     la, lo = ll(200, 150, 20.0, 250.0, 0.25, 0.25)
     out.append(("regional_to_1deg_inside", g_reg, configs.def_L(lib, 30, 20, 25.0, 255.0, 1.0, 1.0), (150, 200), (20, 30), la, lo))
     out.append(("regional_to_1.3deg_outside", g_reg, configs.def_L(lib, 50, 40, 15.0, 245.0, 1.3, 1.3), (150, 200), (40, 50), la, lo))
+    # targets of the other compatible types (gdinterp.c:32-75 admits L, A, B, G): a coarse Gaussian grid and global 'A' / 'B' grids
+    la_g, lo_g = ll(360, 181, -90.0, 0.0, 1.0, 1.0)
+    out.append(("global1deg_to_G48x24", g_glb, lib.ezqkdef(48, 24, "G", 0, 0, 0, 0), (181, 360), (24, 48), la_g, lo_g))
+    out.append(("global1deg_to_A72x36", g_glb, lib.ezqkdef(72, 36, "A", 0, 0, 0, 0), (181, 360), (36, 72), la_g, lo_g))
+    out.append(("global1deg_to_B73x37", g_glb, lib.ezqkdef(73, 37, "B", 0, 0, 0, 0), (181, 360), (37, 73), la_g, lo_g))
     g_gau = lib.ezqkdef(192, 96, "G", 0, 0, 0, 0)
     lat = np.zeros((96, 192), np.float32); lon = np.zeros((96, 192), np.float32)
     lib.gdll(g_gau, lat, lon)
@@ -46,6 +51,8 @@ def test_average_against_oracle(ezb, ezref, cuda_ok, degree):
     try:
         for (pb, pr) in zip(_pairs(ezb), _pairs(ezref)):
             name, gdin_b, gdout_b, ss, ds, la, lo = pb
+            if degree == "sph_average" and "_to_B73" in name:
+                continue   # pole rows: 1 / cos(90 deg) -- the reference walks ~1e8 columns outside its work array (undefined)
             for extrap, value in ((None, None), ("value", -7.5), ("linear", None)):
                 outs = []
                 zin = configs.field(la, lo, k=2).astype(np.float32).reshape(ss)
