@@ -1070,8 +1070,29 @@ bool ensure_fork() {
     return S.fork_ok;
 }
 
+// Scattered ('Y' cloud) targets arrive in arbitrary order: the kernels walk them sorted by source cell (a permutation built once
+// per gridset) so that neighbouring threads gather from the same sectors.  nullptr when it does not apply or cannot be built.
+const int *cloud_target_order(Gset &gs, const InterpArgs &a, const Grid &out) {
+    if (out.grtyp != 'Y' || a.o.arith < 1 || a.npts < 32768 || band_of(out).on) return nullptr;
+    if (!gs.perm_tried) {
+        gs.perm_tried = true;
+        if (cudaMalloc((void **)&gs.d_perm, (size_t)a.npts * sizeof(int)) == cudaSuccess) {
+            const GridDev &sg = a.src;
+            if (!ezk::sort_points_by_cell(gs.d_x, gs.d_y, a.yy ? gs.d_zb : nullptr, sg.ni, sg.j2 - sg.j1 + 1, a.npts, gs.d_perm, S.stream)) {
+                cudaFree(gs.d_perm);
+                gs.d_perm = nullptr;
+            }
+            S.launches += 2;
+        } else {
+            gs.d_perm = nullptr;
+            (void)cudaGetLastError();
+        }
+    }
+    return gs.d_perm;
+}
+
 // Zone list of a gridset for the direct kernel, built on first use (shared by every session: complete before it is published).
-bool ensure_zonelist(Gset &gs, int skip_dehors_only, int npts) {
+bool ensure_zonelist(Gset &gs, int skip_dehors_only, int npts, const int *order = nullptr) {
     const int k = skip_dehors_only ? 1 : 0;
     if (gs.zlist_built[k]) return true;
     const int *c = gs.counts;
@@ -1083,7 +1104,7 @@ bool ensure_zonelist(Gset &gs, int skip_dehors_only, int npts) {
         if (cudaMalloc((void **)&gs.d_zlist[k], (size_t)bound * sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); gs.d_zlist[k] = nullptr; return false; }
         unsigned int n = 0;
         cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), S.stream);
-        ezk::zone_list(gs.d_zb, npts, skip_dehors_only, gs.d_zlist[k], d_cursor, S.stream);
+        ezk::zone_list(gs.d_zb, npts, skip_dehors_only, gs.d_zlist[k], d_cursor, S.stream, order);
         S.launches++;
         if (cudaMemcpyAsync(&n, d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream) != cudaSuccess ||
             cudaStreamSynchronize(S.stream) != cudaSuccess || (long)n > bound) {
@@ -1240,16 +1261,21 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
     // a copy pipeline with one stage to fill) is all there is to such a launch; the direct kernel (ez_interp_fast.cuh) takes it.
     // The choice follows the field count of the API CALL, not of the level chunk or device block at hand, so that a call's
     // result does not depend on how it was cut.  c_ezb200_set_direct_max_fields / EZB200_DIRECT_MAX_FIELDS override (0 = never).
-    if ((S.call_fields > 0 ? S.call_fields : nfields) <= S.direct_max && nfields <= 8 && ezk::direct_eligible(a) && out.grtyp != 'Y') {
+    // ('Y' cloud targets have no tile path: for them the direct kernel replaces the per-point kernel at any field count)
+    const bool direct_few = (S.call_fields > 0 ? S.call_fields : nfields) <= S.direct_max && nfields <= 8 && out.grtyp != 'Y';
+    const bool direct_cloud = out.grtyp == 'Y' && S.direct_max > 0 && !band_of(out).on;
+    if ((direct_few || direct_cloud) && ezk::direct_eligible(a)) {
         const Band band = band_of(out);
         if (band.on && band.j1 <= band.j0) return rc;
         int nz = 0;
         const int *zl = nullptr;
+        a.order = direct_cloud ? cloud_target_order(*gs, a, out) : nullptr;
         if (a.use_zones) {
             const int k = (a.o.extrap >= EZ_MAXIMUM) ? 1 : 0;
-            if (!ensure_zonelist(*gs, k, a.npts)) return -1;
+            if (!ensure_zonelist(*gs, k, a.npts, a.order)) return -1;
             zl = gs->d_zlist[k]; nz = gs->nzlist[k];
         }
+        pre.has_dehors = gs->counts[0] > 0;
         float *zo = d_zout;
         if (band.on) {   // full-grid indexing lands in the band buffer
             a.band_j0 = band.j0; a.band_j1 = band.j1;
@@ -1339,22 +1365,9 @@ int sint_dev(Grid &out, Grid &in, float *d_zout, const float *d_zin, int nfields
         }
     }
     // scattered ('Y' cloud) targets arrive in arbitrary order: the per-point kernel walks them sorted by source cell
-    if (!a.tiles && out.grtyp == 'Y' && a.o.arith >= 1 && a.npts >= 32768 && !band_of(out).on) {
-        if (!gs->perm_tried) {
-            gs->perm_tried = true;
-            if (cudaMalloc((void **)&gs->d_perm, (size_t)a.npts * sizeof(int)) == cudaSuccess) {
-                const GridDev &sg = a.src;
-                if (!ezk::sort_points_by_cell(gs->d_x, gs->d_y, a.yy ? gs->d_zb : nullptr, sg.ni, sg.j2 - sg.j1 + 1, a.npts, gs->d_perm, S.stream)) {
-                    cudaFree(gs->d_perm);
-                    gs->d_perm = nullptr;
-                }
-                S.launches += 2;
-            } else {
-                gs->d_perm = nullptr;
-                (void)cudaGetLastError();
-            }
-        }
-        if (gs->d_perm) { a.list = gs->d_perm; a.nlist = a.npts; }
+    if (!a.tiles) {
+        const int *perm = cloud_target_order(*gs, a, out);
+        if (perm) { a.list = perm; a.nlist = a.npts; }
     }
     const Band band = band_of(out);
     if (band.on) {

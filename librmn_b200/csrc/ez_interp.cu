@@ -1002,7 +1002,7 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
     // The per-field scalars (pole means, extrapolation value) and the zone points that read them are small, latency-bound
     // launches: with fork resources they run beside the direct kernel (disjoint target points) instead of around it.  A
     // constant extrapolation value is read by the direct kernel itself: then the scalars stay in front of it.
-    const bool direct_reads_fs = a.fs && !a.o.vector && a.o.extrap >= EZ_MAXIMUM;
+    const bool direct_reads_fs = a.fs && !a.o.vector && a.o.extrap >= EZ_MAXIMUM && (!pre || pre->has_dehors);
     const bool conc = fork && !timing && nzlist > 0 && !direct_reads_fs;   // (per-kernel timing: everything in line on s)
     cudaStream_t s_list = s;
     if (timing) cudaEventRecord(timing->ev[0], s);
@@ -1038,9 +1038,9 @@ int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_
     return launches;
 }
 
-void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s) {
+void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s, const int *order) {
     if (npts <= 0) return;
-    k_zone_list<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(zb, npts, skip_dehors_only, list, cursor);
+    k_zone_list<<<(npts + TPB - 1) / TPB, TPB, 0, s>>>(zb, npts, skip_dehors_only, list, cursor, order);
 }
 
 int interp_avg(const InterpArgs &a, const float *row_lat, int sph, const int *zlist, int nzlist, cudaStream_t s) {

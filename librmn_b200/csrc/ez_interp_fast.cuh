@@ -306,8 +306,9 @@ __device__ __forceinline__ void point_body(const GridDev &g, const InterpArgs &a
                                            uint8_t zbits) {
     const long is = a.in_stride, os = a.out_stride;
     // the compacted list is short and its points are expensive (zone points): levels are split over blockIdx.y
-    const int f0 = a.list ? blockIdx.y * LIST_LCH : 0;
-    const int nf = a.list ? min(LIST_LCH, a.nfields - f0) : a.nfields;
+    const int lch = a.list_lch > 0 ? a.list_lch : LIST_LCH;
+    const int f0 = a.list ? blockIdx.y * lch : 0;
+    const int nf = a.list ? min(lch, a.nfields - f0) : a.nfields;
     float *zo = a.zout + n + f0 * os;
     z += f0 * is;
     if (zbits == 0) {
@@ -496,18 +497,24 @@ __global__ void __launch_bounds__(TPB, DEG == 1 ? EZ_DIRECT_MINB_LIN : EZ_DIRECT
     const int nb = n0 + blockIdx.x * (TPB * PPT) + threadIdx.x;
     float px[PPT], py[PPT];
     uint8_t bits[PPT];
+    int pt[PPT];   // target point of slot k (through the walking order of a scattered target), -1 = none
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        const int n = nb + k * TPB;
-        const bool in = n < n1;
+        const int m = nb + k * TPB;
+        pt[k] = m < n1 ? (a.order ? __ldg(a.order + m) : m) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int n = pt[k];
+        const bool in = n >= 0;
         px[k] = in ? a.x[n] : 1.f;
         py[k] = in ? a.y[n] : 1.f;
         bits[k] = (in && a.zb) ? a.zb[n] : (uint8_t)0;
     }
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        const int n = nb + k * TPB;
-        if (n >= n1) continue;
+        const int n = pt[k];
+        if (n < 0) continue;
         const uint8_t zbits = a.use_zones ? (uint8_t)(bits[k] & 0x1f) : (uint8_t)0;
         if (zbits) {
             if (zbits == ZB_DEHORS && a.o.extrap >= EZ_MAXIMUM) {
@@ -524,10 +531,12 @@ __global__ void __launch_bounds__(TPB, DEG == 1 ? EZ_DIRECT_MINB_LIN : EZ_DIRECT
 }
 
 // the points with zone bits (optionally without those that are outside the source and nothing else), compacted
+// (order: walk the points of a scattered target in their source-cell order, so that the list comes out roughly sorted as well)
 __global__ void __launch_bounds__(TPB) k_zone_list(const uint8_t *__restrict__ zb, int npts, int skip_dehors_only, int *__restrict__ list,
-                                                   unsigned int *__restrict__ cursor) {
-    const int n = blockIdx.x * TPB + threadIdx.x;
-    const uint8_t z = (n < npts) ? (uint8_t)(zb[n] & 0x1f) : (uint8_t)0;
+                                                   unsigned int *__restrict__ cursor, const int *__restrict__ order) {
+    const int t = blockIdx.x * TPB + threadIdx.x;
+    const int n = (t < npts) ? (order ? order[t] : t) : 0;
+    const uint8_t z = (t < npts) ? (uint8_t)(zb[n] & 0x1f) : (uint8_t)0;
     const bool take = z != 0 && !(skip_dehors_only && z == ZB_DEHORS);
     const unsigned int ballot = __ballot_sync(0xffffffffu, take);
     if (!ballot) return;
@@ -545,12 +554,20 @@ bool direct_args_ok(const InterpArgs &a) {
     return true;
 }
 
-bool launch_fast(const InterpArgs &a, cudaStream_t s) {
-    if (a.src.xpn != XPN_NONE || a.src.yinv) return false;
-    if (a.yy && (a.src2.xpn != XPN_NONE || a.src2.yinv)) return false;
-    const int nbx = ((a.list ? a.nlist : a.npts) + TPB - 1) / TPB;
+bool launch_fast(const InterpArgs &a0, cudaStream_t s) {
+    if (a0.src.xpn != XPN_NONE || a0.src.yinv) return false;
+    if (a0.yy && (a0.src2.xpn != XPN_NONE || a0.src2.yinv)) return false;
+    const int nbx = ((a0.list ? a0.nlist : a0.npts) + TPB - 1) / TPB;
     if (nbx <= 0) return true;
-    const dim3 nb(nbx, a.list ? (a.nfields + LIST_LCH - 1) / LIST_LCH : 1);
+    // A short list (a few zone points of a many-level call) is one CTA's latency chain: fewer levels per thread, down to one, until
+    // there are some 64 K point-levels per chunk; long lists keep LIST_LCH levels per thread (the per-point plan is not free).
+    InterpArgs a = a0;
+    if (a.list && a.list_lch <= 0) {
+        const long per = ((long)a.nlist * a.nfields + 65535) / 65536;
+        a.list_lch = (int)(per < 1 ? 1 : (per > LIST_LCH ? LIST_LCH : per));
+    }
+    const int lch = a.list_lch > 0 ? a.list_lch : LIST_LCH;
+    const dim3 nb(nbx, a.list ? (a.nfields + lch - 1) / lch : 1);
     switch (a.o.degree) {
         case EZ_NEAREST: k_interp_fast<0><<<nb, TPB, 0, s>>>(a); return true;
         case EZ_AVERAGE: case EZ_SPH_AVERAGE:   // zone points of an average only (interp_avg): the zone branch does not depend on DEG

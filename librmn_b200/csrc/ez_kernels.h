@@ -46,9 +46,12 @@ struct InterpArgs {
     // per-point kernel restricted to a compacted list of target points (nullptr = all npts points)
     const int *list;
     int nlist;
+    int list_lch;           // levels per thread when the kernel runs on a list (set by the launcher; 0 = the default chunk)
     // tiled path with a constant extrapolation value: the points outside the source (and in no other zone), taken off `list`
     const int *clist;
     int nclist;
+    // direct kernel on a scattered ('Y' cloud) target: the order in which the points are walked (sorted by source cell), or nullptr
+    const int *order;
     // direct kernel, c_ezuvint of one pair: cached grid-to-grid wind rotation (ez_wind.cu), applied to fields (0, 1) before the store
     const float4 *wrot;
 };
@@ -111,6 +114,7 @@ bool direct_eligible(const InterpArgs &a);
 // pre: the per-field scalars pre-pass of this launch (field_scalars), issued by interp_direct so that it can run beside the kernel
 struct DirectPre {
     bool run;
+    bool has_dehors;   // the gridset has points outside the source (only then does the direct kernel itself read the scalars)
     int need_poles, need_minmax;
     FieldScalars *fs;
     unsigned int *scratch;
@@ -118,7 +122,7 @@ struct DirectPre {
 // timing (c_ezb200_set_timing): events around [scalars pre-pass | direct kernel | zone-list kernel], all in line on s
 int interp_direct(const InterpArgs &a, const int *zlist, int nzlist, cudaStream_t s, const InterpFork *fork = nullptr, const DirectPre *pre = nullptr,
                   const InterpTiming *timing = nullptr);
-void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s);
+void zone_list(const uint8_t *zb, int npts, int skip_dehors_only, int *list, unsigned int *cursor, cudaStream_t s, const int *order = nullptr);
 // interp_degree = average / sph_average (ez_avg.inc, ez_avg_sph.inc): every target point, then ez_corrval on the zone list.
 // row_lat: latitudes of the target points (first column read), sph_average only
 int interp_avg(const InterpArgs &a, const float *row_lat, int sph, const int *zlist, int nzlist, cudaStream_t s);
