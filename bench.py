@@ -570,7 +570,7 @@ def main():
 
     extra = {}
     if full and world == 1 and args.workload == "c2" and args.arith == 2 and not args.levels:
-        for key, (wl, ar) in (("c3_ezuvint", ("c3", 2)), ("c1_ezsint", ("c1", 2)), ("c5", ("c5", 2)), ("c2_arith1_fp64", ("c2", 1))):
+        for key, (wl, ar) in (("c3_ezuvint", ("c3", 2)), ("c1_ezsint", ("c1", 2)), ("c4_cloud_target", ("c4", 2)), ("c5", ("c5", 2)), ("c2_arith1_fp64", ("c2", 1))):
             try:
                 extra[key] = sub_record(measure(B, wl, ar, args.steps, args.warmup, 0, rank, world, stream, sustain_s=0.5, pageable=(wl != "c2"), parity=True))
             except SystemExit as ex:
