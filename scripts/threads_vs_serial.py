@@ -1,3 +1,4 @@
+"""Threaded against serial calls on shared grids, with the number and location of differing values (the diagnostic behind\ntests/test_threads_gpu.py).  usage: python scripts/threads_vs_serial.py"""
 import sys, os, threading
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import numpy as np
