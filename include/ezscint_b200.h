@@ -185,7 +185,8 @@ int32_t c_ezb200_set_devices(int32_t n);
  * the direct kernel (one thread per target point, no per-tile set-up; for one (u, v) pair the grid-to-grid wind rotation is
  * applied before the store); larger calls run on the tile kernels, whose set-up is amortised over the levels.  Both evaluate the
  * same fp32 difference form from the same plans and agree within rounding of the field's local variation (~1e-7 of its range).
- * Default 4 (environment: EZB200_DIRECT_MAX_FIELDS); 0 = tile kernels for every call.  Per calling thread; returns the previous value. */
+ * Scattered ('Y' cloud) targets, which have no tile path, take the direct kernel at any field count (in source-cell order).
+ * Default 4 (environment: EZB200_DIRECT_MAX_FIELDS); 0 = never the direct kernel.  Per calling thread; returns the previous value. */
 int32_t c_ezb200_set_direct_max_fields(int32_t n);
 int32_t c_ezb200_sync(void);
 const char *c_ezb200_version(void);
